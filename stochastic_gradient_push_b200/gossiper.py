@@ -1,0 +1,330 @@
+"""
+Gossipers: one consensus-averaging step over the current graph window.
+
+API parity with ``gossip/gossiper.py`` -- ``Gossiper`` (:31-173), ``PushSum``
+(:176-219), ``PushPull`` (:222-275), ``BilatPushPull`` (:278-323): same
+constructor, ``mix()`` signatures/returns, ``ps_weight`` / ``peers_per_itr``
+properties, ``refresh_peers_``, ``refresh_mixing_weights_``, ``mix_out_msg_``,
+``clean_msg_buffers_``, ``parse_in_msg_buffer`` and the public attributes
+(``in_msg_buffer``, ``placeholder``, ``out_msg_buffer``, ``out_edges``,
+``in_edges``, ``mixing_weights``, ``passive``, ``regular``, ``device``).
+
+What is different underneath:
+
+* The reference emulates point-to-point with ``dist.broadcast`` inside one
+  2-rank process group per edge.  Here a gossiper owns a *transport*:
+
+  - ``PeerMemoryTransport`` (CUDA, ``ops/peer_mix.py``): the message lives in
+    NVSwitch-mapped symmetric memory and ``mix`` is ONE sm_100a kernel that
+    publishes the message, waits on the in-neighbours' sequence flags and
+    accumulates their buffers with weighted 16-byte P2P loads.  No NCCL.
+  - ``C10dTransport`` (any backend, CPU/gloo capable): true ``isend/irecv``
+    on the world group.  It is the portable fallback and the numerical oracle
+    for the kernels.
+
+* Because receives are posted before sends and nothing blocks on a peer's
+  *matching call order*, PushPull cannot deadlock on non-bipartite graphs
+  (the reference deadlocks on gloo for e.g. a ring); the
+  active/passive distinction is kept as an attribute for API parity only.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .topology.graph_manager import GraphManager
+from .mixing_manager import MixingManager, UniformMixing
+
+
+# --------------------------------------------------------------------------- #
+# transports
+# --------------------------------------------------------------------------- #
+class C10dTransport(object):
+    """isend/irecv on a c10d group.  Tags disambiguate repeated edges between
+    the same pair inside one step (phone books may contain duplicates)."""
+
+    name = 'c10d'
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def post_recvs(self, buffers, in_edges):
+        reqs, seen = [], {}
+        for buf, edge in zip(buffers, in_edges):
+            k = seen.get(edge.src, 0)
+            seen[edge.src] = k + 1
+            reqs.append(dist.irecv(buf, src=edge.src, group=self.group, tag=k))
+        return reqs
+
+    def post_sends(self, msgs, out_edges):
+        reqs, seen = [], {}
+        for msg, edge in zip(msgs, out_edges):
+            k = seen.get(edge.dest, 0)
+            seen[edge.dest] = k + 1
+            reqs.append(dist.isend(msg, dst=edge.dest, group=self.group, tag=k))
+        return reqs
+
+    def post_polled_recv(self, buf, in_edge):
+        """A receive whose completion can be polled without blocking.  gloo's
+        ``Work.is_completed()`` never flips until ``wait()`` is called, so a
+        helper thread parks in ``wait()`` and raises an event instead."""
+        return _PolledRecv(self.post_recvs([buf], [in_edge])[0])
+
+
+class _PolledRecv(object):
+
+    def __init__(self, req):
+        import threading
+        self._req = req
+        self._done = threading.Event()
+        self._err = None
+        self._thread = threading.Thread(target=self._park, daemon=True,
+                                        name='Gossip-Recv-Poll')
+        self._thread.start()
+
+    def _park(self):
+        try:
+            self._req.wait()
+        except Exception as e:       # surfaced to the caller in wait()
+            self._err = e
+        self._done.set()
+
+    def is_completed(self):
+        return self._done.is_set()
+
+    def wait(self):
+        self._done.wait()
+        if self._err is not None:
+            raise self._err
+
+
+# --------------------------------------------------------------------------- #
+# base class
+# --------------------------------------------------------------------------- #
+class Gossiper(object):
+    """Generic multi-peer gossip averaging object."""
+
+    def __init__(self, msg, graph, device=None, mixing=None, logger=None,
+                 rank=None, world_size=None, transport=None):
+        self.logger = logger
+        if rank is None or world_size is None:
+            assert dist.is_initialized(), \
+                'pass rank/world_size or initialise torch.distributed'
+            rank, world_size = dist.get_rank(), dist.get_world_size()
+        self.rank = rank
+        self.world_size = world_size
+        assert isinstance(graph, GraphManager)
+        self._graph_manager = graph
+        self.device = torch.device(device) if device is not None else msg.device
+        self.passive = self._graph_manager.is_passive()
+        self.refresh_peers_(rotate=False)
+
+        if mixing is None:
+            mixing = UniformMixing(self._graph_manager, self.device)
+        assert isinstance(mixing, MixingManager)
+        self._mixing_manager = mixing
+        self.refresh_mixing_weights_()
+        self.regular = self._mixing_manager.is_regular()
+
+        self.out_msg_buffer = []
+        self._ps_weight = torch.ones(1, dtype=msg.dtype, device=self.device)
+        numel = msg.numel() + (0 if self.regular else 1)
+        self.in_msg_buffer = torch.zeros(numel, dtype=msg.dtype, device=self.device)
+        self.in_msg_buffer[:msg.numel()].copy_(msg.detach().reshape(-1))
+        if not self.regular:
+            self.in_msg_buffer[-1] = 1.0
+        if self.device.type == 'cpu' and torch.cuda.is_available():
+            try:
+                self.in_msg_buffer = self.in_msg_buffer.pin_memory()
+            except Exception as e:          # pragma: no cover
+                if self.logger is not None:
+                    self.logger.error(e)
+        self.placeholder = self.in_msg_buffer.clone()
+        self._extra_placeholders = []
+        self._pending_req = None
+        self.transport = transport if transport is not None else C10dTransport()
+
+    # -- properties --------------------------------------------------------- #
+    @property
+    def ps_weight(self):
+        return self._ps_weight
+
+    @ps_weight.setter
+    def ps_weight(self, v):
+        if torch.is_tensor(v):
+            self._ps_weight.copy_(v.reshape(-1)[:1])
+        else:
+            self._ps_weight.fill_(float(v))
+
+    @property
+    def peers_per_itr(self):
+        return self._graph_manager.peers_per_itr
+
+    @peers_per_itr.setter
+    def peers_per_itr(self, v):
+        self._graph_manager.peers_per_itr = v
+        # the reference leaves a stale `peers_per_itr_device` and stale edges
+        # behind here; we refresh so the new window is live
+        self.refresh_peers_(rotate=False)
+
+    @property
+    def peers_per_itr_device(self):
+        return torch.tensor([self._graph_manager.peers_per_itr],
+                            device=self.device, dtype=self._ps_weight.dtype)
+
+    # -- graph / weights ---------------------------------------------------- #
+    def refresh_peers_(self, rotate=None):
+        if rotate is None:
+            rotate = self._graph_manager.is_dynamic_graph()
+        assert not (rotate and not self._graph_manager.is_dynamic_graph())
+        self.out_edges, self.in_edges = self._graph_manager.get_edges(rotate)
+
+    def refresh_mixing_weights_(self, residual_adjusted=False):
+        self.mixing_weights = self._mixing_manager.get_mixing_weights(
+            residual_adjusted)
+
+    def _weight(self, key, dtype):
+        return self.mixing_weights[key].to(device=self.device, dtype=dtype)
+
+    def mix_out_msg_(self, out_msg, ps_weight, residual=False):
+        """Generator of outgoing messages: optional loop-back first, then one
+        message per out-edge.  Uniform mixing scales ``out_msg`` IN PLACE and
+        yields the same tensor for every edge (reference semantics,
+        ``gossip/gossiper.py:139-143``)."""
+        self.refresh_mixing_weights_(residual)
+        self.ps_weight = ps_weight
+        if not self.regular:
+            out_msg = torch.cat([out_msg.reshape(-1),
+                                 self.ps_weight.to(out_msg.dtype)])
+        if not residual:
+            yield out_msg.mul(self._weight('lo', out_msg.dtype))
+        if self._mixing_manager.is_uniform():
+            out_msg *= self._weight('uniform', out_msg.dtype)
+            for _ in self.out_edges:
+                yield out_msg
+        else:
+            for edge in self.out_edges:
+                yield out_msg.mul(self._weight(edge.dest, out_msg.dtype))
+
+    def clean_msg_buffers_(self):
+        """Wait for every in-flight send, then drop the references."""
+        while self.out_msg_buffer:
+            req, _ = self.out_msg_buffer.pop()
+            req.wait()
+
+    def parse_in_msg_buffer(self, residual=False):
+        msg = self.in_msg_buffer
+        if not self.regular:
+            return msg.narrow(0, 0, len(msg) - 1), msg[-1]
+        if residual:
+            return msg, self.ps_weight * self.peers_per_itr_device
+        return msg, torch.ones(1, device=self.device, dtype=msg.dtype)
+
+    # -- shared exchange ---------------------------------------------------- #
+    def _recv_buffers(self, k):
+        while len(self._extra_placeholders) < k - 1:
+            self._extra_placeholders.append(torch.empty_like(self.placeholder))
+        return ([self.placeholder] + self._extra_placeholders)[:k]
+
+    def _exchange(self, out_msg, ps_weight, residual):
+        """post irecvs -> post isends -> wait -> accumulate."""
+        assert out_msg.device.type == self.device.type
+        msgs = self.mix_out_msg_(out_msg, ps_weight, residual)
+        loopback = None if residual else next(msgs)
+
+        remote_in = [e for e in self.in_edges if e.src != e.dest]
+        bufs = self._recv_buffers(len(remote_in))
+        recv_reqs = self.transport.post_recvs(bufs, remote_in)
+
+        self_msgs, send_edges, send_msgs = [], [], []
+        for edge in self.out_edges:
+            m = next(msgs)
+            if edge.dest == edge.src:      # self-edge (e.g. n=2, ppi=2)
+                self_msgs.append(m)
+            else:
+                send_edges.append(edge)
+                send_msgs.append(m)
+        for req, m in zip(self.transport.post_sends(send_msgs, send_edges),
+                          send_msgs):
+            self.out_msg_buffer.append((req, m))
+
+        if loopback is not None:
+            self.in_msg_buffer.copy_(loopback)
+        else:
+            self.in_msg_buffer.zero_()
+        for m in self_msgs:
+            self.in_msg_buffer.add_(m)
+        for req, buf in zip(recv_reqs, bufs):
+            req.wait()
+            self.in_msg_buffer.add_(buf)
+
+        self.refresh_peers_()
+        self.clean_msg_buffers_()
+        return self.parse_in_msg_buffer(residual)
+
+    def mix(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+class PushSum(Gossiper):
+    """Column-stochastic push (SGP).  ``mix(out_msg, ps_weight, residual)``
+    returns ``(in_msg, in_ps_weight)``; with ``residual=True`` the result is
+    the sum of what the in-neighbours pushed (the caller folds it into its own
+    pre-scaled copy), otherwise it already contains the ``lo``-weighted
+    loop-back."""
+
+    def mix(self, out_msg, ps_weight, residual=False):
+        if self.logger is not None:
+            self.logger.debug('in/out -peers {}/{}'.format(
+                self.in_edges, self.out_edges))
+        return self._exchange(out_msg, ps_weight, residual)
+
+
+class PushPull(Gossiper):
+    """Doubly-stochastic symmetric exchange (D-PSGD)."""
+
+    def mix(self, out_msg, ps_weight, residual=False):
+        if self.logger is not None:
+            self.logger.debug('in/out -peers {}/{}'.format(
+                self.in_edges, self.out_edges))
+        return self._exchange(out_msg, ps_weight, residual)
+
+
+class BilatPushPull(Gossiper):
+    """Bilateral exchange for AD-PSGD: active ranks send then receive; passive
+    ranks keep one receive posted, poll it, and answer only once the partner's
+    message has landed.  Returns ``(in_msg, ps_weight)`` on completion and
+    ``(out_msg, False)`` when a passive rank has nothing yet (callers test the
+    truthiness of the second element, ``gossip/ad_psgd.py:354-356``)."""
+
+    def mix(self, out_msg):
+        assert out_msg.device.type == self.device.type
+        assert len(self.in_edges) == 1 and len(self.out_edges) == 1
+        out_edge, in_edge = self.out_edges[0], self.in_edges[0]
+
+        if not self.passive:
+            msg = next(self.mix_out_msg_(out_msg, 1., residual=True))
+            recv = self.transport.post_recvs([self.in_msg_buffer], [in_edge])
+            send = self.transport.post_sends([msg], [out_edge])
+            send[0].wait()
+            recv[0].wait()
+            completed = True
+        else:
+            if self._pending_req is None:
+                self._pending_req = self.transport.post_polled_recv(
+                    self.in_msg_buffer, in_edge)
+            if self._pending_req.is_completed():
+                self._pending_req.wait()
+                msg = next(self.mix_out_msg_(out_msg, 1., residual=True))
+                self.transport.post_sends([msg], [out_edge])[0].wait()
+                self._pending_req = None
+                completed = True
+            else:
+                completed = False
+
+        if completed:
+            self.refresh_peers_()
+            self.clean_msg_buffers_()
+            return self.parse_in_msg_buffer(residual=True)
+        return out_msg, completed

@@ -1,0 +1,348 @@
+// Python bindings + native runtime for the gossip data plane.
+//
+//  * SymmetricBuffer: cudaMalloc'd, IPC-exportable device memory wrapped as a
+//    torch tensor; peers open it with cudaIpcOpenMemHandle and read it with
+//    plain loads over NVLink/NVSwitch (one rendezvous replaces the reference's
+//    O(world * schedule) two-rank process groups, gossip/graph_manager.py:27).
+//  * GossipContext: owns the SgpArgs block for one (parameter arena, peer
+//    table, schedule) triple and launches the kernels on the current stream.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sgp_common.cuh"
+
+namespace py = pybind11;
+
+#define SGP_CUDA_CHECK(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess)                                                      \
+            throw std::runtime_error(std::string(#expr) + " failed: " +             \
+                                     cudaGetErrorString(_e));                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// symmetric memory
+// ---------------------------------------------------------------------------
+static py::tuple symm_alloc(int64_t nbytes, int device)
+{
+    c10::cuda::CUDAGuard guard(device);
+    void* ptr = nullptr;
+    // round up to 2 MiB so the allocation owns whole pages (IPC exports pages)
+    const int64_t gran = 2ll << 20;
+    const int64_t padded = (nbytes + gran - 1) / gran * gran;
+    SGP_CUDA_CHECK(cudaMalloc(&ptr, padded));
+    SGP_CUDA_CHECK(cudaMemset(ptr, 0, padded));
+    SGP_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t handle;
+    std::string hbytes;
+    cudaError_t e = cudaIpcGetMemHandle(&handle, ptr);
+    if (e == cudaSuccess) {
+        hbytes.assign(reinterpret_cast<const char*>(&handle), sizeof(handle));
+    } else {
+        (void)cudaGetLastError();   // single-process use still works without IPC
+    }
+    auto opts = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, device);
+    auto t = torch::from_blob(ptr, {nbytes}, [device](void* p) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        cudaFree(p);
+        cudaSetDevice(cur);
+    }, opts);
+    return py::make_tuple(t, py::bytes(hbytes));
+}
+
+static torch::Tensor symm_open(const std::string& hbytes, int64_t nbytes, int device)
+{
+    if (hbytes.size() != sizeof(cudaIpcMemHandle_t))
+        throw std::runtime_error("symm_open: bad IPC handle size");
+    c10::cuda::CUDAGuard guard(device);
+    cudaIpcMemHandle_t handle;
+    std::memcpy(&handle, hbytes.data(), sizeof(handle));
+    void* ptr = nullptr;
+    SGP_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+    auto opts = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, device);
+    return torch::from_blob(ptr, {nbytes}, [device](void* p) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        cudaIpcCloseMemHandle(p);
+        cudaSetDevice(cur);
+    }, opts);
+}
+
+// same-process peer (one process driving several GPUs, or loop-back tests)
+static bool enable_peer_access(int device, int peer)
+{
+    if (device == peer) return true;
+    c10::cuda::CUDAGuard guard(device);
+    int can = 0;
+    SGP_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return false;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return true; }
+    SGP_CUDA_CHECK(e);
+    return true;
+}
+
+// pinned host word the probe kernel can write (AD-PSGD passive poll)
+static torch::Tensor pinned_flag()
+{
+    return torch::zeros({16}, torch::TensorOptions().dtype(torch::kInt32).pinned_memory(true));
+}
+
+// ---------------------------------------------------------------------------
+// GossipContext
+// ---------------------------------------------------------------------------
+class GossipContext {
+public:
+    GossipContext(torch::Tensor z, c10::optional<torch::Tensor> g, c10::optional<torch::Tensor> m,
+                  c10::optional<torch::Tensor> shadow, c10::optional<torch::Tensor> residual,
+                  torch::Tensor pad_ptrs, c10::optional<torch::Tensor> outbox_ptrs,
+                  torch::Tensor table, torch::Tensor wtable, int rank, int world,
+                  torch::Tensor state, torch::Tensor hyper, double timeout_s)
+    {
+        TORCH_CHECK(z.is_cuda() && z.scalar_type() == torch::kFloat32 && z.is_contiguous(),
+                    "z must be a contiguous fp32 CUDA tensor");
+        TORCH_CHECK(z.numel() % SGP_CHUNK == 0, "arena length must be a multiple of ", SGP_CHUNK);
+        TORCH_CHECK(world >= 1 && world <= SGP_MAX_RANKS, "world size out of range");
+        TORCH_CHECK(table.scalar_type() == torch::kInt32 && table.size(1) == SGP_TABLE_ROW);
+        TORCH_CHECK(wtable.scalar_type() == torch::kFloat32 && wtable.size(1) == SGP_WTABLE_ROW);
+        TORCH_CHECK(table.size(0) == wtable.size(0));
+        TORCH_CHECK(pad_ptrs.scalar_type() == torch::kInt64 && pad_ptrs.numel() == world);
+        TORCH_CHECK(state.numel() * state.element_size() >= (int64_t)sizeof(SgpState));
+        TORCH_CHECK(hyper.numel() * hyper.element_size() >= (int64_t)sizeof(SgpHyper));
+        device_ = z.get_device();
+        std::memset(&args_, 0, sizeof(args_));
+        args_.z = z.data_ptr<float>();
+        args_.n = z.numel();
+        keep_.push_back(z);
+        if (g.has_value() && g->defined()) {
+            TORCH_CHECK(g->numel() == z.numel() && g->is_contiguous());
+            TORCH_CHECK(g->scalar_type() == torch::kFloat32 || g->scalar_type() == torch::kBFloat16);
+            args_.g = g->data_ptr();
+            grad_bf16_ = g->scalar_type() == torch::kBFloat16;
+            keep_.push_back(*g);
+        }
+        if (m.has_value() && m->defined()) {
+            TORCH_CHECK(m->numel() == z.numel() && m->scalar_type() == torch::kFloat32);
+            args_.m = m->data_ptr<float>();
+            keep_.push_back(*m);
+        }
+        if (shadow.has_value() && shadow->defined()) {
+            TORCH_CHECK(shadow->numel() == z.numel() && shadow->scalar_type() == torch::kBFloat16);
+            args_.shadow = reinterpret_cast<__nv_bfloat16*>(shadow->data_ptr());
+            keep_.push_back(*shadow);
+        }
+        if (residual.has_value() && residual->defined()) {
+            TORCH_CHECK(residual->numel() == z.numel() && residual->scalar_type() == torch::kFloat32);
+            args_.residual = residual->data_ptr<float>();
+            keep_.push_back(*residual);
+        }
+        args_.pads = reinterpret_cast<SgpSignalPad* const*>(pad_ptrs.data_ptr<int64_t>());
+        keep_.push_back(pad_ptrs);
+        if (outbox_ptrs.has_value() && outbox_ptrs->defined()) {
+            TORCH_CHECK(outbox_ptrs->scalar_type() == torch::kInt64 && outbox_ptrs->numel() == world);
+            args_.outboxes = reinterpret_cast<float* const*>(outbox_ptrs->data_ptr<int64_t>());
+            keep_.push_back(*outbox_ptrs);
+        }
+        set_schedule(table, wtable);
+        args_.rank = rank;
+        args_.world = world;
+        args_.st = reinterpret_cast<SgpState*>(state.data_ptr());
+        args_.hyper = reinterpret_cast<const SgpHyper*>(hyper.data_ptr());
+        args_.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+        keep_.push_back(state);
+        keep_.push_back(hyper);
+        max_grid_ = sgp_max_resident_ctas(device_);
+    }
+
+    void set_schedule(torch::Tensor table, torch::Tensor wtable)
+    {
+        TORCH_CHECK(table.is_cuda() && wtable.is_cuda() && table.is_contiguous() && wtable.is_contiguous());
+        args_.table = table.data_ptr<int>();
+        args_.wtable = wtable.data_ptr<float>();
+        args_.period = (int)table.size(0);
+        sched_keep_ = {table, wtable};
+    }
+
+    void set_grad(torch::Tensor g)
+    {
+        TORCH_CHECK(g.numel() == args_.n && g.is_contiguous());
+        TORCH_CHECK(g.scalar_type() == torch::kFloat32 || g.scalar_type() == torch::kBFloat16);
+        args_.g = g.data_ptr();
+        grad_bf16_ = g.scalar_type() == torch::kBFloat16;
+        grad_keep_ = g;
+    }
+
+    int max_grid() const { return max_grid_; }
+
+    void step(unsigned int flags, int grid)
+    {
+        check_grid(grid);
+        SgpArgs a = prepare(flags);
+        if (a.flags & SGP_F_SGD) TORCH_CHECK(a.g && a.m, "SGD needs grad + momentum buffers");
+        if (a.flags & SGP_F_FOLD_RES) TORCH_CHECK(a.residual, "fold needs a residual buffer");
+        if (a.flags & SGP_F_PUBLISH) TORCH_CHECK(a.outboxes, "publish needs outboxes");
+        if (a.flags & SGP_F_PHASE2) TORCH_CHECK(a.flags & SGP_F_PUBLISH, "phase 2 needs publish");
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
+    }
+
+    void gather(int grid, int pub_grid)
+    {
+        check_grid(grid);
+        SgpArgs a = prepare(0);
+        TORCH_CHECK(a.residual && a.outboxes);
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_gather(&a, grid, pub_grid, at::cuda::getCurrentCUDAStream()));
+    }
+
+    void probe(int pub_grid, c10::optional<torch::Tensor> host_flag)
+    {
+        SgpArgs a = prepare(0);
+        uint32_t* hf = nullptr;
+        if (host_flag.has_value() && host_flag->defined()) {
+            void* dev = nullptr;
+            SGP_CUDA_CHECK(cudaHostGetDevicePointer(&dev, host_flag->data_ptr(), 0));
+            hf = reinterpret_cast<uint32_t*>(dev);
+        }
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_probe(&a, pub_grid, hf, at::cuda::getCurrentCUDAStream()));
+    }
+
+    void allreduce_sgd(torch::Tensor grad_ptrs, unsigned int flags, int grid)
+    {
+        check_grid(grid);
+        SgpArgs a = prepare(flags);
+        TORCH_CHECK(a.m, "allreduce_sgd needs a momentum buffer");
+        TORCH_CHECK(grad_ptrs.scalar_type() == torch::kInt64 && grad_ptrs.numel() == a.world);
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_allreduce_sgd(
+            &a, reinterpret_cast<void* const*>(grad_ptrs.data_ptr<int64_t>()), grid,
+            at::cuda::getCurrentCUDAStream()));
+    }
+
+    void barrier()
+    {
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_barrier(args_.pads, args_.st, args_.rank, args_.world,
+                                          args_.timeout_ns, at::cuda::getCurrentCUDAStream()));
+    }
+
+    void set_timeout(double seconds) { args_.timeout_ns = (unsigned long long)(seconds * 1e9); }
+
+private:
+    SgpArgs prepare(unsigned int flags) const
+    {
+        SgpArgs a = args_;
+        a.flags = flags;
+        if (grad_bf16_) a.flags |= SGP_F_GRAD_BF16; else a.flags &= ~SGP_F_GRAD_BF16;
+        if (!a.shadow) a.flags &= ~SGP_F_SHADOW;
+        return a;
+    }
+    void check_grid(int grid) const
+    {
+        TORCH_CHECK(grid >= 1 && grid <= SGP_MAX_CTAS, "grid out of range");
+        TORCH_CHECK(max_grid_ == 0 || grid <= max_grid_,
+                    "grid ", grid, " exceeds the co-resident capacity ", max_grid_,
+                    " (flag-waiting CTAs must all be resident)");
+    }
+
+    SgpArgs args_;
+    int device_ = 0;
+    int max_grid_ = 0;
+    bool grad_bf16_ = false;
+    std::vector<torch::Tensor> keep_;
+    std::vector<torch::Tensor> sched_keep_;
+    torch::Tensor grad_keep_;
+};
+
+static void scale_(torch::Tensor x, torch::Tensor scalar, bool invert,
+                   c10::optional<torch::Tensor> shadow)
+{
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kFloat32 && x.is_contiguous());
+    TORCH_CHECK(x.numel() % 4 == 0);
+    TORCH_CHECK(scalar.is_cuda() && scalar.scalar_type() == torch::kFloat32);
+    __nv_bfloat16* sh = nullptr;
+    if (shadow.has_value() && shadow->defined())
+        sh = reinterpret_cast<__nv_bfloat16*>(shadow->data_ptr());
+    c10::cuda::CUDAGuard guard(x.get_device());
+    SGP_CUDA_CHECK(sgp_launch_scale(x.data_ptr<float>(), x.numel(), scalar.data_ptr<float>(),
+                                    invert ? 1 : 0, sh, at::cuda::getCurrentCUDAStream()));
+}
+
+static void zero_(torch::Tensor x)
+{
+    TORCH_CHECK(x.is_cuda() && x.is_contiguous());
+    const int64_t bytes = x.numel() * x.element_size();
+    TORCH_CHECK(bytes % 16 == 0);
+    c10::cuda::CUDAGuard guard(x.get_device());
+    SGP_CUDA_CHECK(sgp_launch_zero(x.data_ptr(), bytes, at::cuda::getCurrentCUDAStream()));
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
+{
+    mod.doc() = "sm_100a gossip kernels + symmetric-memory runtime";
+    mod.def("symm_alloc", &symm_alloc, "allocate IPC-exportable device memory -> (uint8 tensor, handle)");
+    mod.def("symm_open", &symm_open, "map a peer's allocation -> uint8 tensor");
+    mod.def("enable_peer_access", &enable_peer_access);
+    mod.def("pinned_flag", &pinned_flag);
+    mod.def("scale_", &scale_, py::arg("x"), py::arg("scalar"), py::arg("invert"),
+            py::arg("shadow") = py::none());
+    mod.def("zero_", &zero_);
+    mod.def("max_resident_ctas", &sgp_max_resident_ctas);
+
+    mod.attr("CHUNK") = (int)SGP_CHUNK;
+    mod.attr("MAX_PEERS") = (int)SGP_MAX_PEERS;
+    mod.attr("MAX_RANKS") = (int)SGP_MAX_RANKS;
+    mod.attr("MAX_CTAS") = (int)SGP_MAX_CTAS;
+    mod.attr("TABLE_ROW") = (int)SGP_TABLE_ROW;
+    mod.attr("WTABLE_ROW") = (int)SGP_WTABLE_ROW;
+    mod.attr("PAD_BYTES") = (int)sizeof(SgpSignalPad);
+    mod.attr("STATE_BYTES") = (int)sizeof(SgpState);
+    mod.attr("HYPER_FLOATS") = (int)(sizeof(SgpHyper) / sizeof(float));
+    mod.attr("STATE_OFF_STEP") = (int)offsetof(SgpState, step);
+    mod.attr("STATE_OFF_STATUS") = (int)offsetof(SgpState, status);
+    mod.attr("STATE_OFF_PSW") = (int)offsetof(SgpState, ps_weight);
+    mod.attr("STATE_OFF_RESW") = (int)offsetof(SgpState, res_weight);
+    mod.attr("STATE_OFF_PHASE_BASE") = (int)offsetof(SgpState, phase_base);
+    mod.attr("STATE_OFF_ACK_FROM") = (int)offsetof(SgpState, ack_from);
+    mod.attr("STATE_OFF_BILAT_DONE") = (int)offsetof(SgpState, bilat_done);
+    mod.attr("F_SGD") = (unsigned)SGP_F_SGD;
+    mod.attr("F_SHADOW") = (unsigned)SGP_F_SHADOW;
+    mod.attr("F_ZERO_GRAD") = (unsigned)SGP_F_ZERO_GRAD;
+    mod.attr("F_PHASE1") = (unsigned)SGP_F_PHASE1;
+    mod.attr("F_PHASE2") = (unsigned)SGP_F_PHASE2;
+    mod.attr("F_FOLD_RES") = (unsigned)SGP_F_FOLD_RES;
+    mod.attr("F_NO_ROTATE") = (unsigned)SGP_F_NO_ROTATE;
+    mod.attr("F_PUBLISH") = (unsigned)SGP_F_PUBLISH;
+
+    py::class_<GossipContext>(mod, "GossipContext")
+        .def(py::init<torch::Tensor, c10::optional<torch::Tensor>, c10::optional<torch::Tensor>,
+                      c10::optional<torch::Tensor>, c10::optional<torch::Tensor>, torch::Tensor,
+                      c10::optional<torch::Tensor>, torch::Tensor, torch::Tensor, int, int,
+                      torch::Tensor, torch::Tensor, double>(),
+             py::arg("z"), py::arg("g"), py::arg("m"), py::arg("shadow"), py::arg("residual"),
+             py::arg("pad_ptrs"), py::arg("outbox_ptrs"), py::arg("table"), py::arg("wtable"),
+             py::arg("rank"), py::arg("world"), py::arg("state"), py::arg("hyper"),
+             py::arg("timeout_s") = 30.0)
+        .def("set_schedule", &GossipContext::set_schedule)
+        .def("set_grad", &GossipContext::set_grad)
+        .def("set_timeout", &GossipContext::set_timeout)
+        .def("max_grid", &GossipContext::max_grid)
+        .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))
+        .def("gather", &GossipContext::gather, py::arg("grid"), py::arg("pub_grid"))
+        .def("probe", &GossipContext::probe, py::arg("pub_grid"), py::arg("host_flag") = py::none())
+        .def("allreduce_sgd", &GossipContext::allreduce_sgd)
+        .def("barrier", &GossipContext::barrier);
+}

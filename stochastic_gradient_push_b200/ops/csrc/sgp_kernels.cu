@@ -1,0 +1,583 @@
+// sm_100a gossip kernels: fused SGD + push-sum mix over NVSwitch peer memory.
+//
+// Replaces, in ONE launch per training step, the reference's K1-K9 elementwise
+// swarm (ps_numerator / unbias / residual add / pre-scale / flatten / scale /
+// accumulate / unflatten / optimizer.step; gossip/distributed.py:298-455,
+// gossip/gossiper.py:125-219, gossip_sgd.py:389) and its N1-N3 NCCL broadcasts.
+//
+//   sgp_step_kernel    phase 1: x = z*w ; SGD-momentum ; (+residual) ; publish
+//                      phase 2: acquire in-neighbours' flags ; weighted P2P
+//                               loads ; push-sum weight update ; de-bias ; store
+//   sgp_gather_kernel  Overlap-SGP: residual = sum_k w_k * outbox_k  (side stream)
+//   sgp_probe_kernel   AD-PSGD passive poll ("has my partner published?")
+//   sgp_allreduce_sgd  AR-SGD comparator: one-shot P2P all-reduce fused with SGD
+//   sgp_barrier_kernel device-side barrier over the signal pads
+//   sgp_scale_kernel   flat x *= w  /  x /= w  (ps_numerator / unbias API parity)
+#include "sgp_common.cuh"
+
+namespace {
+
+struct RowInfo {
+    int   n_in, n_out;
+    int   in[SGP_MAX_PEERS];
+    int   out[SGP_MAX_PEERS];
+    float self_w;
+    float in_w[SGP_MAX_PEERS];
+};
+
+__device__ __forceinline__ void load_row(const SgpArgs& a, uint32_t step_like, RowInfo& r) {
+    const uint32_t row = (step_like + a.st->phase_base) % (uint32_t)a.period;
+    const int*   t = a.table  + row * SGP_TABLE_ROW;
+    const float* w = a.wtable + row * SGP_WTABLE_ROW;
+    r.n_in = t[0];
+    r.n_out = t[1];
+#pragma unroll
+    for (int k = 0; k < SGP_MAX_PEERS; ++k) {
+        r.in[k]   = t[2 + k];
+        r.out[k]  = t[2 + SGP_MAX_PEERS + k];
+        r.in_w[k] = w[1 + k];
+    }
+    r.self_w = w[0];
+}
+
+__device__ __forceinline__ float4 fma4(float4 a, float s, float4 b) {
+    return make_float4(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z), fmaf(a.w, s, b.w));
+}
+__device__ __forceinline__ float4 mul4(float4 a, float s) {
+    return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+
+// SGD with momentum on the push-sum numerator (torch.optim.SGD semantics,
+// dampening 0): d = g + wd*x ; m = mu*m + d ; x -= lr * (nesterov ? d + mu*m : m)
+__device__ __forceinline__ void sgd1(float& x, float g, float& m, float lr, float mu,
+                                     float wd, float nesterov) {
+    const float d = fmaf(wd, x, g);
+    m = fmaf(mu, m, d);
+    const float upd = (nesterov != 0.f) ? fmaf(mu, m, d) : m;
+    x = fmaf(-lr, upd, x);
+}
+
+// Last-CTA bookkeeping shared by the kernels: returns true in thread 0 of the
+// CTA that finishes last.
+__device__ __forceinline__ bool cta_done_is_last(SgpState* st) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(&st->done_ctas, 1u);
+    if (prev == gridDim.x - 1) {
+        __threadfence();
+        return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Fused step kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SGP_THREADS, 2)
+sgp_step_kernel(const SgpArgs a)
+{
+    __shared__ float s_wn;        // new push-sum weight
+    __shared__ int   s_ok;
+
+    SgpState* st = a.st;
+    const uint32_t step   = *((volatile uint32_t*)&st->step);
+    const uint32_t parity = step & 1u;
+    const uint32_t flags  = a.flags;
+    const int      tid    = threadIdx.x;
+    const int      b      = blockIdx.x;
+    const long long nchunks = a.n / SGP_CHUNK;
+
+    RowInfo row;
+    load_row(a, step, row);
+
+    const float w0 = *((volatile float*)&st->ps_weight[parity]);
+    const float wres = (flags & SGP_F_FOLD_RES) ? *((volatile float*)&st->res_weight) : 0.f;
+    const float w1 = w0 + wres;                    // weight of the published numerator
+
+    SgpSignalPad* mypad = a.pads[a.rank];
+    float* my_out = a.outboxes ? (a.outboxes[a.rank] + (size_t)parity * a.n) : nullptr;
+
+    const SgpHyper hp = *a.hyper;
+    const uint64_t pol_first = l2_evict_first_policy();
+    const uint64_t pol_last = l2_evict_last_policy();
+    const bool do_sgd = (flags & SGP_F_SGD) && (hp.do_sgd != 0.f);
+
+    // ---------------- phase 1: local update + publish ----------------------
+    if (flags & SGP_F_PHASE1) {
+        if ((flags & SGP_F_PUBLISH) && step >= st->ack_from + 2u) {
+            // WAR fence: outbox[parity] was last read at step-2 by that step's
+            // out-neighbours; wait for their acks before overwriting it.
+            if (tid == 0) {
+                RowInfo prev;
+                load_row(a, step - 2u, prev);
+                int ok = 1;
+                for (int k = 0; k < prev.n_out; ++k) {
+                    const int o = prev.out[k];
+                    if (o == a.rank || o < 0) continue;
+                    ok &= spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns,
+                                        SGP_ERR_TIMEOUT_ACK) ? 1 : 0;
+                }
+                s_ok = ok;
+            }
+            __syncthreads();
+        }
+
+        const float inv_w1 = 1.f / w1;
+        const bool write_z = !(flags & SGP_F_PHASE2);
+
+        for (long long c = b; c < nchunks; c += gridDim.x) {
+            const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+            float4 x[SGP_UNROLL], g[SGP_UNROLL], m[SGP_UNROLL], r[SGP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) {
+                const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                x[u] = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
+                if (do_sgd) {
+                    if (flags & SGP_F_GRAD_BF16)
+                        g[u] = bf16x4_to_f4(ld_once_u2(reinterpret_cast<const uint2*>(
+                                   reinterpret_cast<const __nv_bfloat16*>(a.g) + i), pol_first));
+                    else
+                        g[u] = ld_once_f4(reinterpret_cast<const float4*>(
+                                   reinterpret_cast<const float*>(a.g) + i), pol_first);
+                    m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
+                }
+                if (flags & SGP_F_FOLD_RES)
+                    r[u] = ld_once_f4(reinterpret_cast<const float4*>(a.residual + i), pol_first);
+            }
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) {
+                const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                float4 xv = mul4(x[u], w0);                 // numerator (exact if w0 == 1)
+                if (do_sgd) {
+                    float4 gv = mul4(g[u], hp.grad_scale);
+                    float4 mv = m[u];
+                    sgd1(xv.x, gv.x, mv.x, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                    sgd1(xv.y, gv.y, mv.y, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                    sgd1(xv.z, gv.z, mv.z, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                    sgd1(xv.w, gv.w, mv.w, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                    st_f4(reinterpret_cast<float4*>(a.m + i), mv);
+                    if (flags & SGP_F_ZERO_GRAD) {
+                        if (flags & SGP_F_GRAD_BF16)
+                            st_u2(reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.g) + i),
+                                  make_uint2(0u, 0u));
+                        else
+                            st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g) + i),
+                                  make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                }
+                if (flags & SGP_F_FOLD_RES) {
+                    xv.x += r[u].x; xv.y += r[u].y; xv.z += r[u].z; xv.w += r[u].w;
+                }
+                if (flags & SGP_F_PUBLISH)   // keep the outbox in L2 for phase 2 / peers
+                    st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
+                if (write_z) {
+                    const float4 zv = mul4(xv, inv_w1);
+                    st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                    if (flags & SGP_F_SHADOW)
+                        st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                }
+            }
+        }
+
+        if (flags & SGP_F_PUBLISH) {
+            __syncthreads();
+            if (tid == 0) {
+                st_relaxed_sys_f32(&mypad->psw[parity], w1);   // same value from every CTA
+                __threadfence_system();
+                st_release_sys(&mypad->pub_seq[b], step + 1u);
+            }
+        }
+    }
+
+    float w_next = (flags & SGP_F_PUBLISH) ? row.self_w * w1 : w1;
+
+    // ---------------- phase 2: pull + mix ----------------------------------
+    if (flags & SGP_F_PHASE2) {
+        if (tid == 0) {
+            int ok = 1;
+            float wn = row.self_w * w1;
+            for (int k = 0; k < row.n_in; ++k) {
+                const int j = row.in[k];
+                if (j < 0) continue;
+                const SgpSignalPad* pj = a.pads[j];
+                ok &= spin_wait_geq(&pj->pub_seq[b], step + 1u, st, a.timeout_ns,
+                                    SGP_ERR_TIMEOUT_PUB) ? 1 : 0;
+                wn = fmaf(row.in_w[k], ld_relaxed_sys_f32(&pj->psw[parity]), wn);
+            }
+            s_wn = wn;
+            s_ok = ok;
+        }
+        __syncthreads();
+        const float wn = s_wn;
+        w_next = wn;
+        if (s_ok) {
+            const float inv_wn = 1.f / wn;
+            const float* peer_out[SGP_MAX_PEERS];
+#pragma unroll
+            for (int k = 0; k < SGP_MAX_PEERS; ++k)
+                peer_out[k] = (k < row.n_in && row.in[k] >= 0)
+                                  ? a.outboxes[row.in[k]] + (size_t)parity * a.n : nullptr;
+
+            // reverse order: the chunks this CTA published last are still in L2
+            const long long my_chunks = (nchunks > b) ? (nchunks - 1 - b) / gridDim.x + 1 : 0;
+            for (long long it = my_chunks - 1; it >= 0; --it) {
+                const long long c = b + it * gridDim.x;
+                const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+                float4 acc[SGP_UNROLL];
+                float4 pv[SGP_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) {
+                    const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                    acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first),
+                                  row.self_w);
+                }
+                // peer loads: all UNROLL requests of one peer in flight together
+                for (int k = 0; k < row.n_in; ++k) {
+                    const float* po = peer_out[k];
+                    if (po == nullptr) continue;
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        pv[u] = ld_stream_f4(reinterpret_cast<const float4*>(po + i));
+                    }
+                    const float wk = row.in_w[k];
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(pv[u], wk, acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) {
+                    const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                    const float4 zv = mul4(acc[u], inv_wn);
+                    st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                    if (flags & SGP_F_SHADOW)
+                        st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                }
+            }
+        }
+    }
+
+    // ---------------- epilogue: last CTA publishes state + acks ------------
+    __syncthreads();
+    if (tid == 0 && cta_done_is_last(st)) {
+        if (flags & SGP_F_PHASE2) {
+            for (int k = 0; k < row.n_in; ++k) {
+                const int j = row.in[k];
+                if (j < 0 || j == a.rank) continue;
+                st_release_sys(&a.pads[j]->ack_seq[a.rank], step + 1u);
+            }
+        }
+        const bool rotate = !(flags & SGP_F_NO_ROTATE);
+        *((volatile float*)&st->ps_weight[rotate ? (parity ^ 1u) : parity]) = w_next;
+        if (flags & SGP_F_FOLD_RES) *((volatile float*)&st->res_weight) = 0.f;
+        *((volatile uint32_t*)&st->done_ctas) = 0u;
+        if (rotate) *((volatile uint32_t*)&st->step) = step + 1u;
+        __threadfence();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Overlap-SGP gather: residual = sum_k in_w[k] * outbox_k[parity]   (side stream)
+// Runs after the local publish kernel of the same step, i.e. st->step == s+1.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SGP_THREADS, 2)
+sgp_gather_kernel(const SgpArgs a, const int pub_grid)
+{
+    __shared__ int s_ok;
+    SgpState* st = a.st;
+    const uint32_t s      = *((volatile uint32_t*)&st->step) - 1u;
+    const uint32_t parity = s & 1u;
+    const int tid = threadIdx.x;
+    const long long nchunks = a.n / SGP_CHUNK;
+
+    RowInfo row;
+    load_row(a, s, row);
+
+    // every CTA waits for ALL publisher CTAs of every in-neighbour (block-parallel poll)
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    for (int k = 0; k < row.n_in; ++k) {
+        const int j = row.in[k];
+        if (j < 0) continue;
+        const SgpSignalPad* pj = a.pads[j];
+        for (int f = tid; f < pub_grid; f += SGP_THREADS)
+            if (!spin_wait_geq(&pj->pub_seq[f], s + 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_PUB))
+                s_ok = 0;
+    }
+    __syncthreads();
+
+    if (s_ok) {
+        const float* peer_out[SGP_MAX_PEERS];
+#pragma unroll
+        for (int k = 0; k < SGP_MAX_PEERS; ++k)
+            peer_out[k] = (k < row.n_in && row.in[k] >= 0)
+                              ? a.outboxes[row.in[k]] + (size_t)parity * a.n : nullptr;
+        for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+            float4 acc[SGP_UNROLL], pv[SGP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < row.n_in; ++k) {
+                const float* po = peer_out[k];
+                if (po == nullptr) continue;
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u)
+                    pv[u] = ld_stream_f4(reinterpret_cast<const float4*>(
+                                po + base + (long long)u * SGP_THREADS * SGP_VEC));
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(pv[u], row.in_w[k], acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u)
+                st_f4(reinterpret_cast<float4*>(a.residual + base +
+                                                (long long)u * SGP_THREADS * SGP_VEC), acc[u]);
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0 && cta_done_is_last(st)) {
+        float wr = 0.f;
+        for (int k = 0; k < row.n_in; ++k) {
+            const int j = row.in[k];
+            if (j < 0) continue;
+            wr = fmaf(row.in_w[k], ld_relaxed_sys_f32(&a.pads[j]->psw[parity]), wr);
+            if (j != a.rank) st_release_sys(&a.pads[j]->ack_seq[a.rank], s + 1u);
+        }
+        *((volatile float*)&st->res_weight) = s_ok ? wr : 0.f;
+        *((volatile uint32_t*)&st->done_ctas) = 0u;
+        __threadfence();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// AD-PSGD passive poll: did the in-neighbour of the current round publish?
+// ---------------------------------------------------------------------------
+__global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* host_flag)
+{
+    __shared__ int s_all;
+    SgpState* st = a.st;
+    const uint32_t step = *((volatile uint32_t*)&st->step);
+    RowInfo row;
+    load_row(a, step, row);
+    if (threadIdx.x == 0) s_all = 1;
+    __syncthreads();
+    for (int k = 0; k < row.n_in; ++k) {
+        const int j = row.in[k];
+        if (j < 0) continue;
+        for (int f = threadIdx.x; f < pub_grid; f += blockDim.x)
+            if ((int32_t)(ld_acquire_sys(&a.pads[j]->pub_seq[f]) - (step + 1u)) < 0) s_all = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->bilat_done = (uint32_t)s_all;
+        if (host_flag) *((volatile uint32_t*)host_flag) = (uint32_t)s_all;
+        __threadfence_system();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// AR-SGD comparator: one-shot P2P all-reduce of the (symmetric) gradient
+// buffers fused with the SGD update.  Every rank sums in rank order, so the
+// replicas stay bit-identical.  pub_seq doubles as the "gradients ready"
+// barrier, ack_seq as the "done reading" barrier.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SGP_THREADS, 2)
+sgp_allreduce_sgd_kernel(const SgpArgs a, void* const* grad_peers)
+{
+    __shared__ int s_ok;
+    SgpState* st = a.st;
+    const uint32_t step = *((volatile uint32_t*)&st->step);
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const uint32_t flags = a.flags;
+    const long long nchunks = a.n / SGP_CHUNK;
+    SgpSignalPad* mypad = a.pads[a.rank];
+    const SgpHyper hp = *a.hyper;
+    const uint64_t pol_first = l2_evict_first_policy();
+
+    // gradients of this rank were produced by earlier kernels on this stream
+    if (tid == 0) {
+        s_ok = 1;
+        __threadfence_system();
+        st_release_sys(&mypad->pub_seq[b], step + 1u);
+    }
+    __syncthreads();
+    if (tid < a.world && tid != a.rank)
+        if (!spin_wait_geq(&a.pads[tid]->pub_seq[b], step + 1u, st, a.timeout_ns,
+                           SGP_ERR_TIMEOUT_PUB))
+            s_ok = 0;
+    __syncthreads();
+
+    if (s_ok) {
+        const float inv_world = hp.grad_scale / (float)a.world;
+        for (long long c = b; c < nchunks; c += gridDim.x) {
+            const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+            float4 acc[SGP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < a.world; ++r) {
+                float4 gv[SGP_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) {
+                    const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                    if (flags & SGP_F_GRAD_BF16) {
+                        uint2 raw;
+                        const uint2* p = reinterpret_cast<const uint2*>(
+                            reinterpret_cast<const __nv_bfloat16*>(grad_peers[r]) + i);
+                        asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                                     : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+                        gv[u] = bf16x4_to_f4(raw);
+                    } else {
+                        gv[u] = ld_stream_f4(reinterpret_cast<const float4*>(
+                            reinterpret_cast<const float*>(grad_peers[r]) + i));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) {
+                    acc[u].x += gv[u].x; acc[u].y += gv[u].y;
+                    acc[u].z += gv[u].z; acc[u].w += gv[u].w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) {
+                const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                float4 xv = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
+                float4 mv = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
+                const float4 gv = mul4(acc[u], inv_world);
+                sgd1(xv.x, gv.x, mv.x, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                sgd1(xv.y, gv.y, mv.y, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                sgd1(xv.z, gv.z, mv.z, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                sgd1(xv.w, gv.w, mv.w, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                st_f4(reinterpret_cast<float4*>(a.m + i), mv);
+                st_f4(reinterpret_cast<float4*>(a.z + i), xv);
+                if (flags & SGP_F_SHADOW)
+                    st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(xv));
+            }
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0 && cta_done_is_last(st)) {
+        // tell every peer we are done with its gradients, then wait until every
+        // peer is done with ours (the next backward overwrites them)
+        for (int r = 0; r < a.world; ++r)
+            if (r != a.rank) st_release_sys(&a.pads[r]->ack_seq[a.rank], step + 1u);
+        for (int r = 0; r < a.world; ++r)
+            if (r != a.rank)
+                spin_wait_geq(&mypad->ack_seq[r], step + 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_ACK);
+        *((volatile uint32_t*)&st->done_ctas) = 0u;
+        *((volatile uint32_t*)&st->step) = step + 1u;
+        __threadfence();
+    }
+}
+
+// after the all-reduce the caller's gradient buffer is cleared by this rank
+__global__ void __launch_bounds__(SGP_THREADS)
+sgp_zero_kernel(float4* p, long long n16)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
+         i += (long long)gridDim.x * blockDim.x)
+        p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// Device barrier across ranks (model.block())
+// ---------------------------------------------------------------------------
+__global__ void sgp_barrier_kernel(SgpSignalPad* const* pads, SgpState* st, int rank, int world,
+                                   unsigned long long timeout_ns)
+{
+    const uint32_t epoch = st->bar_epoch + 1u;
+    const int t = threadIdx.x;
+    __threadfence_system();
+    if (t < world) st_release_sys(&pads[t]->bar_seq[rank], epoch);   // tell everyone
+    if (t < world)
+        spin_wait_geq(&pads[rank]->bar_seq[t], epoch, st, timeout_ns, SGP_ERR_TIMEOUT_BAR);
+    __syncthreads();
+    if (t == 0) { st->bar_epoch = epoch; __threadfence(); }
+}
+
+// ---------------------------------------------------------------------------
+// x *= s  or  x /= s  over a flat buffer (ps_numerator / unbias parity path)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SGP_THREADS)
+sgp_scale_kernel(float* x, long long n, const float* scalar, int invert, __nv_bfloat16* shadow)
+{
+    const float s = invert ? (1.f / *scalar) : *scalar;
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        v = mul4(v, s);
+        reinterpret_cast<float4*>(x)[i] = v;
+        if (shadow) reinterpret_cast<uint2*>(shadow)[i] = f4_to_bf16x4(v);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+extern "C" {
+
+cudaError_t sgp_launch_step(const SgpArgs* args, int grid, cudaStream_t stream)
+{
+    sgp_step_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream)
+{
+    sgp_gather_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args, pub_grid);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_flag,
+                             cudaStream_t stream)
+{
+    sgp_probe_kernel<<<1, SGP_THREADS, 0, stream>>>(*args, pub_grid, host_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_allreduce_sgd(const SgpArgs* args, void* const* grad_peers, int grid,
+                                     cudaStream_t stream)
+{
+    sgp_allreduce_sgd_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args, grad_peers);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_zero(void* p, long long bytes, cudaStream_t stream)
+{
+    const long long n16 = bytes / 16;
+    int grid = (int)((n16 + SGP_THREADS - 1) / SGP_THREADS);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    sgp_zero_kernel<<<grid, SGP_THREADS, 0, stream>>>(reinterpret_cast<float4*>(p), n16);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_barrier(SgpSignalPad* const* pads, SgpState* st, int rank, int world,
+                               unsigned long long timeout_ns, cudaStream_t stream)
+{
+    sgp_barrier_kernel<<<1, SGP_MAX_RANKS, 0, stream>>>(pads, st, rank, world, timeout_ns);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_scale(float* x, long long n, const float* scalar, int invert,
+                             __nv_bfloat16* shadow, cudaStream_t stream)
+{
+    long long n4 = n / 4;
+    int grid = (int)((n4 + SGP_THREADS - 1) / SGP_THREADS);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    sgp_scale_kernel<<<grid, SGP_THREADS, 0, stream>>>(x, n, scalar, invert, shadow);
+    return cudaGetLastError();
+}
+
+int sgp_max_resident_ctas(int device)
+{
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgp_step_kernel, SGP_THREADS, 0)
+        != cudaSuccess) return 0;
+    return sms * per_sm;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+"""
+GossipEngine: drives the sm_100a gossip kernels for ONE rank.
+
+It owns the peer-visible signal pad + double-buffered outbox (symmetric
+memory), the device-side schedule tables emitted from a ``GraphManager`` /
+``MixingManager`` pair, the device-resident hyper-parameters and kernel state,
+and exposes the four launches the algorithms are built from:
+
+    mix(sgd)            SGP / D-PSGD step: [SGD] + publish + pull + mix + de-bias
+    publish(sgd, fold)  Overlap-SGP, main stream: [SGD] + fold residual + publish
+    gather()            Overlap-SGP, side stream: residual = sum of P2P loads
+    local(sgd, fold)    no communication: [SGD] / fold only (flush, world==1)
+
+All launches go to the *current* CUDA stream and are CUDA-graph capturable:
+nothing that changes per step (phase, parity, lr, push-sum weight) is a kernel
+argument -- it all lives in device memory.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native
+
+
+def build_tables(graph, mixing, device):
+    """(table int32 [period, TABLE_ROW], wtable fp32 [period, WTABLE_ROW]).
+
+    ``wtable[t] = [self_w, in_w_0..]`` where ``in_w_k`` is the weight the k-th
+    in-neighbour assigns to its edge towards this rank at phase t, i.e. the
+    receiver evaluates the sender's column of the mixing matrix (the senders
+    never scale a message; reference K6 disappears)."""
+    from ..topology.graph_manager import MAX_PEERS_PER_ITR as MP
+    table = graph.device_table(device=None)
+    period = table.shape[0]
+    sched = graph._schedule
+    k = graph.nprocs_per_node
+    rows = []
+    phases_self = graph.phases()
+    per_rank_phases = {}
+    for t in range(period):
+        outs, ins = phases_self[t]
+        self_w, _ = mixing.scalar_weights([p * k for p in outs])
+        row = [float(self_w)]
+        for j in ins:
+            if j not in per_rank_phases:
+                ph = sched.phases(rank=j)
+                per_rank_phases[j] = ph if graph.is_dynamic_graph() else ph[:1]
+            outs_j = per_rank_phases[j][t][0]
+            _, edge_w = mixing.scalar_weights([p * k for p in outs_j])
+            row.append(float(edge_w[graph.rank * k]))
+        row += [0.0] * (1 + MP - len(row))
+        rows.append(row)
+    wtable = torch.tensor(rows, dtype=torch.float32)
+    return table.to(device), wtable.to(device)
+
+
+class GossipEngine(object):
+
+    def __init__(self, world, params_flat: torch.Tensor, graph, mixing, *,
+                 grad: Optional[torch.Tensor] = None,
+                 momentum: Optional[torch.Tensor] = None,
+                 shadow: Optional[torch.Tensor] = None,
+                 with_residual: bool = False,
+                 grid: Optional[int] = None, gather_grid: Optional[int] = None,
+                 timeout_s: float = 30.0, name: str = 'sgp'):
+        C = native.load()
+        self.C = C
+        self.world = world
+        self.rank = world.rank
+        self.nranks = world.world
+        self.device = params_flat.device
+        self.n = params_flat.numel()
+        assert params_flat.dtype == torch.float32 and self.n % C.CHUNK == 0
+        self.z = params_flat
+        self.grad = grad
+        self.momentum = momentum
+        self.shadow = shadow
+        self.residual = (torch.zeros(self.n, dtype=torch.float32, device=self.device)
+                         if with_residual else None)
+        self.graph = graph
+        self.mixing = mixing
+        assert graph.world_size == self.nranks, \
+            'graph spans %d ranks, symmetric world has %d' % (graph.world_size, self.nranks)
+
+        # symmetric allocations (collective across the world)
+        self.pad = world.alloc(name + '.pad', C.PAD_BYTES)
+        self.outbox = world.alloc(name + '.outbox', 2 * self.n * 4)
+
+        # local kernel state / hyper-parameters
+        self.state = torch.zeros(C.STATE_BYTES, dtype=torch.uint8, device=self.device)
+        self._state_f32 = self.state.view(torch.float32)
+        self._state_i32 = self.state.view(torch.int32)
+        self._state_f32[C.STATE_OFF_PSW // 4: C.STATE_OFF_PSW // 4 + 2] = 1.0
+        self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32).pin_memory()
+        self._hyper_cache = None
+
+        table, wtable = build_tables(graph, mixing, self.device)
+        self.ctx = C.GossipContext(
+            z=self.z, g=grad, m=momentum, shadow=shadow, residual=self.residual,
+            pad_ptrs=self.pad.table, outbox_ptrs=self.outbox.table,
+            table=table, wtable=wtable, rank=self.rank, world=self.nranks,
+            state=self.state, hyper=self.hyper, timeout_s=float(timeout_s))
+        self.period = table.shape[0]
+        self.max_grid = self.ctx.max_grid()
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        nchunks = self.n // C.CHUNK
+        if grid is None:
+            grid = min(self.max_grid, 2 * sms, C.MAX_CTAS)
+        # every rank must use the same grid: per-CTA publish flags are matched by index
+        self.grid = int(max(1, min(grid, nchunks, C.MAX_CTAS)))
+        if gather_grid is None:
+            gather_grid = min(32, self.grid)
+        self.gather_grid = int(max(1, min(gather_grid, nchunks)))
+        self.steps = 0               # host mirror of SgpState.step
+        self._graph_synced = 0       # rotations applied to the python graph object
+        self.set_hyper(0.0, 0.0, 0.0, False, do_sgd=False)
+        torch.cuda.synchronize(self.device)
+        world.barrier()
+
+    # -- configuration ------------------------------------------------------ #
+    def set_hyper(self, lr, momentum, weight_decay, nesterov, do_sgd=True, grad_scale=1.0):
+        key = (float(lr), float(momentum), float(weight_decay), bool(nesterov),
+               bool(do_sgd), float(grad_scale))
+        if key == self._hyper_cache:
+            return
+        self._hyper_cache = key
+        h = self._hyper_host
+        h[0], h[1], h[2] = key[0], key[1], key[2]
+        h[3] = 1.0 if key[3] else 0.0
+        h[4] = 1.0 if key[4] else 0.0
+        h[5] = key[5]
+        self.hyper.copy_(h, non_blocking=True)
+
+    def set_schedule(self, graph=None, mixing=None):
+        """Re-emit the device tables (e.g. after ``peers_per_itr`` changed).
+        Collective in effect: callers drain their streams and barrier first."""
+        C = self.C
+        self.graph = graph or self.graph
+        self.mixing = mixing or self.mixing
+        table, wtable = build_tables(self.graph, self.mixing, self.device)
+        self.ctx.set_schedule(table, wtable)
+        self.period = table.shape[0]
+        want = self.graph.phase_index()
+        base = (want - self.steps) % self.period
+        self._state_i32[C.STATE_OFF_PHASE_BASE // 4] = int(base)
+        self._state_i32[C.STATE_OFF_ACK_FROM // 4] = int(self.steps)
+        self._graph_synced = self.steps
+
+    def set_grad(self, grad: torch.Tensor):
+        self.grad = grad
+        self.ctx.set_grad(grad)
+
+    # -- launches ------------------------------------------------------------ #
+    def _common(self, sgd, zero_grad):
+        C = self.C
+        f = 0
+        if sgd:
+            f |= C.F_SGD
+            if zero_grad:
+                f |= C.F_ZERO_GRAD
+        if self.shadow is not None:
+            f |= C.F_SHADOW
+        return f
+
+    def mix(self, sgd=False, zero_grad=True):
+        C = self.C
+        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_PUBLISH | C.F_PHASE2
+        self.ctx.step(f, self.grid)
+        self.steps += 1
+
+    def publish(self, sgd=False, fold=False, zero_grad=True):
+        C = self.C
+        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_PUBLISH
+        if fold:
+            f |= C.F_FOLD_RES
+        self.ctx.step(f, self.grid)
+        self.steps += 1
+
+    def gather(self):
+        self.ctx.gather(self.gather_grid, self.grid)
+
+    def local(self, sgd=False, fold=False, zero_grad=True):
+        C = self.C
+        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_NO_ROTATE
+        if fold:
+            f |= C.F_FOLD_RES
+        self.ctx.step(f, self.grid)
+
+    def probe(self, host_flag=None):
+        self.ctx.probe(self.grid, host_flag)
+
+    def barrier(self):
+        self.ctx.barrier()
+
+    # -- host-visible state (each of these synchronises) -------------------- #
+    def sync_graph(self):
+        """Advance the python GraphManager to the device's phase."""
+        if self.graph.is_dynamic_graph():
+            for _ in range(self.steps - self._graph_synced):
+                self.graph.get_peers(rotate=True)
+        self._graph_synced = self.steps
+
+    @property
+    def status(self) -> int:
+        return int(self._state_i32[self.C.STATE_OFF_STATUS // 4].item())
+
+    def check(self):
+        st = self.status
+        if st != 0:
+            names = {1: 'in-neighbour never published (heartbeat timeout)',
+                     2: 'out-neighbour never released the outbox (ack timeout)',
+                     3: 'device barrier timeout'}
+            raise RuntimeError('gossip kernel error on rank %d: %s'
+                               % (self.rank, names.get(st, 'code %d' % st)))
+
+    @property
+    def device_step(self) -> int:
+        return int(self._state_i32[self.C.STATE_OFF_STEP // 4].item())
+
+    @property
+    def ps_weight(self) -> float:
+        off = self.C.STATE_OFF_PSW // 4
+        step = self.device_step
+        return float(self._state_f32[off + (step & 1)].item())
+
+    @ps_weight.setter
+    def ps_weight(self, v: float):
+        off = self.C.STATE_OFF_PSW // 4
+        self._state_f32[off: off + 2] = float(v)
+
+    def ps_weight_tensor(self) -> torch.Tensor:
+        """1-element device tensor view of the CURRENT push-sum weight (no sync
+        of the value itself, but reads the step counter)."""
+        off = self.C.STATE_OFF_PSW // 4
+        return self._state_f32[off + (self.device_step & 1): off + (self.device_step & 1) + 1]
+
+    @property
+    def res_weight(self) -> float:
+        return float(self._state_f32[self.C.STATE_OFF_RESW // 4].item())

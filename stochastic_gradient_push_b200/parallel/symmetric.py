@@ -1,0 +1,144 @@
+"""
+Symmetric (peer-mapped) device memory.
+
+One rendezvous replaces every per-edge NCCL communicator of the reference
+(``gossip/graph_manager.py:22-32`` creates a 2-rank group + 2 warm-up
+all-reduces per phone-book entry): each rank allocates its buffers with the
+native runtime (``_C.symm_alloc`` -> cudaMalloc + cudaIpcGetMemHandle), the
+64-byte handles are exchanged ONCE over the c10d control plane
+(``all_gather_object``; NCCL or gloo, it only moves ~100 bytes), every peer
+maps them (``cudaIpcOpenMemHandle``) and the resulting device pointers are
+packed into an int64 device table that the kernels index by rank.  After that
+NVSwitch makes every peer equidistant; any circulant offset costs the same.
+
+Two worlds implement the same small interface (``alloc`` / ``ptr_table``):
+
+* :class:`SymmetricWorld`   -- one process per GPU (production);
+* :class:`LocalWorld`       -- N virtual ranks inside ONE process (all on one
+  GPU = loop-back tests, or one per visible GPU via plain peer access).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+
+
+class _Buffer(object):
+    __slots__ = ('name', 'nbytes', 'local', 'peers', 'table')
+
+    def __init__(self, name, nbytes):
+        self.name = name
+        self.nbytes = nbytes
+        self.local = None      # uint8 tensor owned by this rank
+        self.peers = None      # list of uint8 tensors (index = rank)
+        self.table = None      # int64 device tensor of base pointers
+
+
+class SymmetricWorld(object):
+    """Symmetric allocator over a ``torch.distributed`` group, one rank per
+    process.  ``ranks`` are the members (global ranks); position in the list
+    is the *symmetric rank* used to index pointer tables."""
+
+    def __init__(self, device=None, group=None):
+        assert dist.is_initialized(), 'SymmetricWorld needs torch.distributed'
+        C = native.load()
+        self._C = C
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        assert self.world <= C.MAX_RANKS
+        self.buffers: Dict[str, _Buffer] = {}
+
+    def alloc(self, name: str, nbytes: int) -> _Buffer:
+        """Collective: every rank allocates ``nbytes`` and maps everyone else's."""
+        assert name not in self.buffers
+        C = self._C
+        buf = _Buffer(name, nbytes)
+        buf.local, handle = C.symm_alloc(int(nbytes), self.device.index)
+        if self.world > 1 and len(handle) == 0:
+            raise RuntimeError('cudaIpcGetMemHandle failed; peer mapping unavailable')
+        gathered = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(gathered, (bytes(handle), int(nbytes)), group=self.group)
+        buf.peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                buf.peers.append(buf.local)
+            else:
+                h, nb = gathered[r]
+                assert nb == nbytes, 'symmetric allocations must have equal size'
+                buf.peers.append(C.symm_open(h, int(nb), self.device.index))
+        buf.table = torch.tensor([t.data_ptr() for t in buf.peers],
+                                 dtype=torch.int64, device=self.device)
+        self.buffers[name] = buf
+        if self.world > 1:
+            dist.barrier(group=self.group)    # nobody touches a peer before all mapped
+        return buf
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+class LocalWorld(object):
+    """``world`` virtual ranks in this process.  ``devices[r]`` is the GPU of
+    virtual rank r (default: all on the current device -> loop-back)."""
+
+    def __init__(self, world: int, devices: Optional[List[int]] = None):
+        C = native.load()
+        self._C = C
+        self.world = world
+        cur = torch.cuda.current_device()
+        self.devices = [cur] * world if devices is None else list(devices)
+        for d in set(self.devices):
+            for p in set(self.devices):
+                if d != p and not C.enable_peer_access(d, p):
+                    raise RuntimeError('no peer access %d -> %d' % (d, p))
+        self.buffers: Dict[str, List[_Buffer]] = {}
+
+    def alloc(self, name: str, nbytes: int) -> List[_Buffer]:
+        C = self._C
+        locals_ = [C.symm_alloc(int(nbytes), d)[0] for d in self.devices]
+        out = []
+        for r, d in enumerate(self.devices):
+            b = _Buffer(name, nbytes)
+            b.local = locals_[r]
+            b.peers = locals_
+            b.table = torch.tensor([t.data_ptr() for t in locals_], dtype=torch.int64,
+                                   device=torch.device('cuda', d))
+            out.append(b)
+        self.buffers[name] = out
+        return out
+
+    def view(self, rank: int) -> '_LocalRankView':
+        return _LocalRankView(self, rank)
+
+
+class _LocalRankView(object):
+    """What one virtual rank sees: same interface as :class:`SymmetricWorld`,
+    with allocations shared through the parent (first caller allocates)."""
+
+    def __init__(self, parent: LocalWorld, rank: int):
+        self.parent = parent
+        self.rank = rank
+        self.world = parent.world
+        self.device = torch.device('cuda', parent.devices[rank])
+        self.group = None
+
+    def alloc(self, name: str, nbytes: int) -> _Buffer:
+        if name not in self.parent.buffers:
+            self.parent.alloc(name, nbytes)
+        b = self.parent.buffers[name][self.rank]
+        assert b.nbytes == nbytes
+        return b
+
+    def barrier(self):
+        torch.cuda.synchronize()

@@ -1,0 +1,101 @@
+"""One process per GPU: IPC rendezvous + P2P kernels over NVLink."""
+import pytest
+import torch
+
+import stochastic_gradient_push_b200 as sgp
+from stochastic_gradient_push_b200.ops import oracle
+
+from dist_utils import run_distributed
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _sgp_worker(rank, world, graph_name, ppi, steps, numel):
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.symmetric import SymmetricWorld
+    from stochastic_gradient_push_b200.ops.peer_mix import GossipEngine
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(1234 + rank)
+    graph = getattr(sgp, graph_name)(rank, world, peers_per_itr=ppi)
+    mixing = sgp.UniformMixing(graph, dev)
+    z = torch.randn(numel, device=dev)
+    grad = torch.randn(numel, device=dev)
+    mom = torch.zeros(numel, device=dev)
+    sw = SymmetricWorld(dev)
+    eng = GossipEngine(sw, z, graph, mixing, grad=grad, momentum=mom, timeout_s=20.0)
+    lr, mu, wd, nest = 0.1, 0.9, 1e-4, True
+    eng.set_hyper(lr, mu, wd, nest)
+
+    # oracle state: every rank simulates the whole world from gathered tensors
+    def gather(t):
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.double() for o in out]
+
+    zs, ms, ws = gather(z), gather(mom), [1.0] * world
+    ogs = [getattr(sgp, graph_name)(r, world, peers_per_itr=ppi) for r in range(world)]
+    oms = [sgp.UniformMixing(g, 'cpu') for g in ogs]
+    for step in range(steps):
+        grad.normal_()
+        gs = gather(grad)
+        torch.cuda.synchronize()
+        eng.mix(sgd=True)
+        torch.cuda.synchronize()
+        eng.check()
+        xs = []
+        for i in range(world):
+            x, ms[i] = oracle.sgd_momentum(zs[i] * ws[i], gs[i], ms[i], lr, mu, wd, nest)
+            xs.append(x)
+        xs, ws = oracle.mix_columns(xs, ws, ogs, oms)
+        oracle.rotate_all(ogs)
+        zs = [x / w for x, w in zip(xs, ws)]
+        torch.testing.assert_close(z.double(), zs[rank], rtol=1e-5, atol=1e-5)
+    return True
+
+
+@pytest.mark.parametrize('graph_name,ppi', [
+    ('NPeerDynamicDirectedExponentialGraph', 1),
+    ('DynamicDirectedExponentialGraph', 2),
+    ('RingGraph', 1),
+])
+def test_sgp_mix_over_nvlink(graph_name, ppi):
+    n = min(_ngpu(), 8)
+    out = run_distributed(_sgp_worker, n, graph_name, ppi, 6, 64 * 4096,
+                          backend='nccl', timeout=300)
+    assert all(out)
+
+
+def _skew_worker(rank, world, steps):
+    """Ranks arrive with random delays; flags + acks must keep data consistent."""
+    import time
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.symmetric import SymmetricWorld
+    from stochastic_gradient_push_b200.ops.peer_mix import GossipEngine
+    dev = torch.device('cuda', rank)
+    graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world)
+    z = torch.full((32 * 4096,), float(rank), device=dev)
+    eng = GossipEngine(SymmetricWorld(dev), z, graph, sgp.UniformMixing(graph, dev), timeout_s=20.0)
+    gen = torch.Generator().manual_seed(rank)
+    total0 = torch.tensor([z.double().sum().item()], device=dev)
+    dist.all_reduce(total0)
+    for _ in range(steps):
+        time.sleep(float(torch.rand(1, generator=gen)) * 0.01)
+        eng.mix(sgd=False)
+    torch.cuda.synchronize()
+    eng.check()
+    assert (z - z[0]).abs().max().item() == 0.0          # every element mixed identically
+    total = torch.tensor([z.double().sum().item()], device=dev)
+    dist.all_reduce(total)
+    assert abs(total.item() - total0.item()) < 1e-3 * abs(total0.item()) + 1e-3
+    return z[0].item()
+
+
+def test_random_skew_conserves_mass():
+    n = min(_ngpu(), 8)
+    out = run_distributed(_skew_worker, n, 40, backend='nccl', timeout=300)
+    mean = sum(range(n)) / n
+    assert all(abs(v - mean) < 1e-3 for v in out)         # 40 steps >> log2(n): consensus
