@@ -59,12 +59,15 @@ def main():
             eng.mix(sgd=False)
         elif args.mode == 'publish':
             eng.publish(sgd=True, fold=True, zero_grad=False)
+            e1.record()
+            eng.gather()            # releases the outbox (acks); not timed
         elif args.mode == 'gather':
             eng.publish(sgd=False)
             eng.gather()
         else:
             eng.local(sgd=True, zero_grad=False)
 
+    e0 = e1 = None
     times = []
     for it in range(args.iters + 3):
         flush.zero_()
@@ -83,7 +86,8 @@ def main():
         else:
             e0.record()
             launch()
-            e1.record()
+            if args.mode != 'publish':
+                e1.record()
         torch.cuda.synchronize()
         if it >= 3:
             times.append(e0.elapsed_time(e1))

@@ -28,9 +28,11 @@ class MixingManager(object):
     def is_uniform(self):
         raise NotImplementedError
 
-    def scalar_weights(self, out_peers=None):
-        """(self_weight, {out_peer_rank: edge_weight}) as floats; the column of
-        the mixing matrix owned by this rank (sums to 1)."""
+    def scalar_weights(self, out_peers=None, rank=None):
+        """(self_weight, {out_peer_rank: edge_weight}) as floats: the column of
+        the mixing matrix owned by ``rank`` (default: this rank) when it pushes
+        to ``out_peers`` (default: the graph's current out-peers).  Columns sum
+        to 1.  Receivers evaluate their in-neighbours' columns with this."""
         raise NotImplementedError
 
     def get_mixing_weights(self, residual_adjusted=True):
@@ -56,7 +58,7 @@ class UniformMixing(MixingManager):
     def is_uniform(self):
         return True
 
-    def scalar_weights(self, out_peers=None):
+    def scalar_weights(self, out_peers=None, rank=None):
         if out_peers is None:
             out_peers, _ = self.graph_manager.get_peers()
         w = 1.0 / (len(out_peers) + 1.0)
@@ -71,9 +73,21 @@ class SelfWeightedMixing(MixingManager):
     reference tree (``gossip/gossiper.py:83-85, 131-132, 163-164``)."""
 
     def __init__(self, graph, device=None, self_weight=0.5):
+        """``self_weight``: float, or a callable / sequence indexed by
+        (node-level) rank for a genuinely non-doubly-stochastic matrix."""
         super().__init__(graph, device)
-        assert 0.0 < self_weight < 1.0
-        self.self_weight = float(self_weight)
+        self.self_weight = self_weight
+
+    def _sw(self, rank):
+        rank = self.graph_manager.rank if rank is None else rank
+        sw = self.self_weight
+        if callable(sw):
+            sw = sw(rank)
+        elif isinstance(sw, (list, tuple)):
+            sw = sw[rank % len(sw)]
+        sw = float(sw)
+        assert 0.0 < sw < 1.0
+        return sw
 
     def is_uniform(self):
         return False
@@ -81,13 +95,14 @@ class SelfWeightedMixing(MixingManager):
     def is_regular(self):
         return False
 
-    def scalar_weights(self, out_peers=None):
+    def scalar_weights(self, out_peers=None, rank=None):
         if out_peers is None:
             out_peers, _ = self.graph_manager.get_peers()
         if not out_peers:
             return 1.0, {}
-        w = (1.0 - self.self_weight) / len(out_peers)
-        return self.self_weight, {p: w for p in out_peers}
+        sw = self._sw(rank)
+        w = (1.0 - sw) / len(out_peers)
+        return sw, {p: w for p in out_peers}
 
 
 MIXING_STRATEGIES = {

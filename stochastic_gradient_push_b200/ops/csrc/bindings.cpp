@@ -184,6 +184,14 @@ public:
         grad_keep_ = g;
     }
 
+    void set_sgd_buffers(torch::Tensor g, torch::Tensor m)
+    {
+        set_grad(g);
+        TORCH_CHECK(m.numel() == args_.n && m.scalar_type() == torch::kFloat32 && m.is_contiguous());
+        args_.m = m.data_ptr<float>();
+        mom_keep_ = m;
+    }
+
     int max_grid() const { return max_grid_; }
 
     void step(unsigned int flags, int grid)
@@ -265,6 +273,7 @@ private:
     std::vector<torch::Tensor> keep_;
     std::vector<torch::Tensor> sched_keep_;
     torch::Tensor grad_keep_;
+    torch::Tensor mom_keep_;
 };
 
 static void scale_(torch::Tensor x, torch::Tensor scalar, bool invert,
@@ -326,6 +335,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
     mod.attr("F_FOLD_RES") = (unsigned)SGP_F_FOLD_RES;
     mod.attr("F_NO_ROTATE") = (unsigned)SGP_F_NO_ROTATE;
     mod.attr("F_PUBLISH") = (unsigned)SGP_F_PUBLISH;
+    mod.attr("F_IN_NUMER") = (unsigned)SGP_F_IN_NUMER;
 
     py::class_<GossipContext>(mod, "GossipContext")
         .def(py::init<torch::Tensor, c10::optional<torch::Tensor>, c10::optional<torch::Tensor>,
@@ -338,6 +348,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
              py::arg("timeout_s") = 30.0)
         .def("set_schedule", &GossipContext::set_schedule)
         .def("set_grad", &GossipContext::set_grad)
+        .def("set_sgd_buffers", &GossipContext::set_sgd_buffers)
         .def("set_timeout", &GossipContext::set_timeout)
         .def("max_grid", &GossipContext::max_grid)
         .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))

@@ -84,6 +84,7 @@ struct SgpHyper {
 #define SGP_F_FOLD_RES   (1u << 6)   // overlap: fold the pending residual in
 #define SGP_F_NO_ROTATE  (1u << 7)   // do not advance step (flush kernels)
 #define SGP_F_PUBLISH    (1u << 8)   // write outbox + release flags
+#define SGP_F_IN_NUMER   (1u << 9)   // z already holds the numerator x (external optimizer)
 
 struct SgpArgs {
     // local buffers (length n, n % SGP_CHUNK == 0)

@@ -92,6 +92,7 @@ sgp_step_kernel(const SgpArgs a)
     load_row(a, step, row);
 
     const float w0 = *((volatile float*)&st->ps_weight[parity]);
+    const float wmul = (flags & SGP_F_IN_NUMER) ? 1.f : w0;   // z -> numerator factor
     const float wres = (flags & SGP_F_FOLD_RES) ? *((volatile float*)&st->res_weight) : 0.f;
     const float w1 = w0 + wres;                    // weight of the published numerator
 
@@ -148,7 +149,7 @@ sgp_step_kernel(const SgpArgs a)
 #pragma unroll
             for (int u = 0; u < SGP_UNROLL; ++u) {
                 const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                float4 xv = mul4(x[u], w0);                 // numerator (exact if w0 == 1)
+                float4 xv = mul4(x[u], wmul);               // numerator (exact if w == 1)
                 if (do_sgd) {
                     float4 gv = mul4(g[u], hp.grad_scale);
                     float4 mv = m[u];

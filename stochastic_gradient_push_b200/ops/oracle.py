@@ -30,7 +30,7 @@ def mix_columns(xs: Sequence[torch.Tensor], ws: Sequence[float], graphs, mixings
     cols = []
     for j in range(n):
         outs, _ = graphs[j].get_peers()
-        cols.append(mixings[j].scalar_weights(outs))
+        cols.append(mixings[j].scalar_weights(outs, rank=j))
     k = graphs[0].nprocs_per_node
     for i in range(n):
         self_w, _ = cols[i]

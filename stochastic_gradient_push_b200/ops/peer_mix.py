@@ -42,14 +42,14 @@ def build_tables(graph, mixing, device):
     per_rank_phases = {}
     for t in range(period):
         outs, ins = phases_self[t]
-        self_w, _ = mixing.scalar_weights([p * k for p in outs])
+        self_w, _ = mixing.scalar_weights([p * k for p in outs], rank=graph.rank)
         row = [float(self_w)]
         for j in ins:
             if j not in per_rank_phases:
                 ph = sched.phases(rank=j)
                 per_rank_phases[j] = ph if graph.is_dynamic_graph() else ph[:1]
             outs_j = per_rank_phases[j][t][0]
-            _, edge_w = mixing.scalar_weights([p * k for p in outs_j])
+            _, edge_w = mixing.scalar_weights([p * k for p in outs_j], rank=j)
             row.append(float(edge_w[graph.rank * k]))
         row += [0.0] * (1 + MP - len(row))
         rows.append(row)
@@ -154,10 +154,14 @@ class GossipEngine(object):
         self.grad = grad
         self.ctx.set_grad(grad)
 
+    def set_sgd_buffers(self, grad: torch.Tensor, momentum: torch.Tensor):
+        self.grad, self.momentum = grad, momentum
+        self.ctx.set_sgd_buffers(grad, momentum)
+
     # -- launches ------------------------------------------------------------ #
-    def _common(self, sgd, zero_grad):
+    def _common(self, sgd, zero_grad, in_numerator=False):
         C = self.C
-        f = 0
+        f = C.F_IN_NUMER if in_numerator else 0
         if sgd:
             f |= C.F_SGD
             if zero_grad:
@@ -166,15 +170,15 @@ class GossipEngine(object):
             f |= C.F_SHADOW
         return f
 
-    def mix(self, sgd=False, zero_grad=True):
+    def mix(self, sgd=False, zero_grad=True, in_numerator=False):
         C = self.C
-        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_PUBLISH | C.F_PHASE2
+        f = self._common(sgd, zero_grad, in_numerator) | C.F_PHASE1 | C.F_PUBLISH | C.F_PHASE2
         self.ctx.step(f, self.grid)
         self.steps += 1
 
-    def publish(self, sgd=False, fold=False, zero_grad=True):
+    def publish(self, sgd=False, fold=False, zero_grad=True, in_numerator=False):
         C = self.C
-        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_PUBLISH
+        f = self._common(sgd, zero_grad, in_numerator) | C.F_PHASE1 | C.F_PUBLISH
         if fold:
             f |= C.F_FOLD_RES
         self.ctx.step(f, self.grid)
@@ -183,9 +187,9 @@ class GossipEngine(object):
     def gather(self):
         self.ctx.gather(self.gather_grid, self.grid)
 
-    def local(self, sgd=False, fold=False, zero_grad=True):
+    def local(self, sgd=False, fold=False, zero_grad=True, in_numerator=False):
         C = self.C
-        f = self._common(sgd, zero_grad) | C.F_PHASE1 | C.F_NO_ROTATE
+        f = self._common(sgd, zero_grad, in_numerator) | C.F_PHASE1 | C.F_NO_ROTATE
         if fold:
             f |= C.F_FOLD_RES
         self.ctx.step(f, self.grid)

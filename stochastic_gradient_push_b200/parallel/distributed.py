@@ -1,0 +1,726 @@
+"""
+GossipDataParallel: SGP / Overlap-SGP / D-PSGD model wrapper.
+
+API parity with ``gossip/distributed.py:39-589`` (constructor arguments,
+``forward``, ``transfer_params``, ``sync_comms``, ``block``, ``state_dict`` /
+``load_state_dict``, ``train`` / ``eval``, ``update_gossiper``,
+``ps_numerator`` / ``unbias``, ``_query_gossip_queue`` and the public
+attributes ``ps_weight``, ``is_ps_numerator``, ``gossip_enable``,
+``gossiping``, ``params_mixed``, ``overlap``, ``synch_freq``, ``asynch``,
+``lazy_mixing``, ``num_updates``, ``dist_config``, ``gossip_stream``).
+
+What is different underneath (B200-first):
+
+* parameters are re-homed into ONE flat, 256-byte aligned arena at wrap time
+  (``utils/arena.py``); there is no per-step flatten / unflatten / per-tensor
+  copy (reference K4/K5/K8).
+* there is no gossip *thread*.  The reference hands the parameters to a Python
+  thread that drives NCCL broadcasts and synchronises a stream
+  (``gossip/distributed.py:459-510``).  Here a gossip step is a kernel launch:
+  in sync mode ONE fused kernel on the current stream, in overlap mode a
+  publish kernel on the current stream plus a gather kernel on
+  ``gossip_stream`` that runs concurrently with the next forward/backward; the
+  "hand-off" is a CUDA event.
+* the push-sum algebra (bias / de-bias / residual add / pre-scale) happens
+  inside those kernels; with :class:`~..optim.FusedGossipSGD` so does the
+  SGD-momentum update (reference K1-K9).
+* on CPU tensors / the gloo backend the same state machine runs over
+  ``isend/irecv`` (``transport='c10d'``), which is also the oracle the kernel
+  path is tested against.
+
+State convention: between launches the parameters always hold the de-biased
+estimate ``z = x / w`` on the kernel transport (``is_ps_numerator`` is only
+True between a backward pass and the next gossip launch when an *external*
+optimizer is used); on the c10d transport they follow the reference's
+numerator / de-biased alternation.
+"""
+
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Variable
+from torch.nn.modules import Module
+
+from ..gossiper import C10dTransport
+from ..mixing_manager import UniformMixing
+from ..topology.graph_manager import NPeerDynamicDirectedExponentialGraph as NPDDEGraph
+from ..utils.arena import FlatArena
+from ..utils.helpers import communicate, create_process_group, group_by_dtype, make_logger
+
+HEARTBEAT_TIMEOUT = 300  # seconds a rank waits for its in-neighbours (reference :36)
+
+
+# --------------------------------------------------------------------------- #
+# backends
+# --------------------------------------------------------------------------- #
+class _KernelBackend(object):
+    """sm_100a data plane: GossipEngine over symmetric memory."""
+
+    name = 'nvlink'
+
+    def __init__(self, owner, arena: FlatArena, graph, mixing, world_view, overlap,
+                 compute_dtype, timeout_s, grid):
+        from ..ops.peer_mix import GossipEngine
+        self.owner = owner
+        self.arena = arena
+        dev = arena.flat.device
+        self.shadow = None
+        if compute_dtype is not None and compute_dtype != torch.float32:
+            assert compute_dtype == torch.bfloat16, 'compute copies are bf16'
+            self.shadow = arena.new_buffer(dtype=torch.bfloat16)
+            self.shadow.copy_(arena.flat)
+        self.engine = GossipEngine(world_view, arena.flat, graph, mixing, shadow=self.shadow,
+                                   with_residual=True, timeout_s=timeout_s, grid=grid,
+                                   name='gdp%d' % owner._instance_id)
+        self.gather_event = None
+        self.residual_pending = False       # a gather finished/launched and is not folded yet
+        self.sgd_pending = False            # FusedGossipSGD.step() deferred into next launch
+        self.has_sgd_buffers = False
+
+    # optimizer buffers are attached lazily by FusedGossipSGD
+    def attach_sgd(self, grad_flat, momentum_flat):
+        self.engine.set_sgd_buffers(grad_flat, momentum_flat)
+        self.has_sgd_buffers = True
+
+
+class _C10dBackend(object):
+    """Portable data plane: isend/irecv of edge-weighted snapshots (+ the
+    push-sum weight as one extra element), residual folded at the next query."""
+
+    name = 'c10d'
+
+    def __init__(self, owner, arenas: Dict[torch.dtype, FlatArena], graph, mixing,
+                 comm_device, group=None):
+        self.owner = owner
+        self.arenas = arenas
+        self.graph = graph
+        self.mixing = mixing
+        self.comm_device = comm_device
+        self.transport = C10dTransport(group)
+        self.pending = None
+        self.send_bufs, self.recv_bufs = {}, {}
+
+    def _buf(self, store, key, numel, dtype):
+        t = store.get(key)
+        if t is None or t.numel() != numel:
+            t = torch.empty(numel, dtype=dtype, device=self.comm_device)
+            if self.comm_device.type == 'cpu' and torch.cuda.is_available():
+                t = t.pin_memory()
+            store[key] = t
+        return t
+
+    def start(self, ps_weight: float, pollable: bool = False):
+        """Snapshot x (numerator, NOT yet self-scaled) and post the exchange.
+        Returns the self-loop weight the caller applies locally."""
+        out_edges, in_edges = self.graph.get_edges()
+        self_w, edge_w = self.mixing.scalar_weights([e.dest for e in out_edges])
+        reqs, recvs, keep, poll = [], [], [], []
+        for dtype, arena in self.arenas.items():
+            n = arena.total + 1
+            remote_in = [e for e in in_edges if e.src != e.dest]
+            bufs = [self._buf(self.recv_bufs, (dtype, i), n, dtype) for i in range(len(remote_in))]
+            if pollable:     # gloo cannot poll a plain irecv (see _PolledRecv)
+                rr = [self.transport.post_polled_recv(b, e) for b, e in zip(bufs, remote_in)]
+            else:
+                rr = self.transport.post_recvs(bufs, remote_in)
+            reqs += rr
+            poll += rr
+            local_add = []
+            send_edges, send_msgs = [], []
+            for i, e in enumerate(out_edges):
+                msg = self._buf(self.send_bufs, (dtype, i), n, dtype)
+                msg[:-1].copy_(arena.flat, non_blocking=True)
+                if self.comm_device.type == 'cpu' and arena.flat.is_cuda:
+                    torch.cuda.current_stream().synchronize()
+                msg[-1] = ps_weight
+                msg.mul_(edge_w[e.dest])
+                if e.dest == e.src:
+                    local_add.append(msg)
+                else:
+                    send_edges.append(e)
+                    send_msgs.append(msg)
+            reqs += self.transport.post_sends(send_msgs, send_edges)
+            recvs.append((arena, bufs + local_add))
+            keep.append(send_msgs)
+        self.pending = (reqs, recvs, keep, poll)
+        if self.graph.is_dynamic_graph():
+            self.graph.get_peers(rotate=True)
+        return self_w
+
+    def done(self) -> bool:
+        if self.pending is None:
+            return True
+        return all(_req_done(r) for r in self.pending[3])
+
+    def finish(self):
+        """Wait and fold: returns the residual push-sum weight."""
+        reqs, recvs, _, _ = self.pending
+        for r in reqs:
+            r.wait()
+        w_res = 0.0
+        first = True
+        for arena, bufs in recvs:
+            for b in bufs:
+                arena.flat.add_(b[:-1].to(arena.flat.device, non_blocking=True))
+                if first:
+                    w_res += float(b[-1])
+            first = False
+        self.pending = None
+        return w_res
+
+
+def _req_done(req) -> bool:
+    try:
+        return bool(req.is_completed())
+    except Exception:
+        return False
+
+
+# --------------------------------------------------------------------------- #
+# wrapper
+# --------------------------------------------------------------------------- #
+_INSTANCES = [0]
+
+
+class GossipDataParallel(Module):
+    """Distributed gossip model wrapper (SGP if ``push_sum`` else D-PSGD;
+    ``overlap=True`` -> OSGP; ``synch_freq>0`` -> bounded-staleness async)."""
+
+    def __init__(self, module, device_ids=None, rank=None, world_size=None,
+                 graph=None, mixing=None, comm_device=None, push_sum=True,
+                 overlap=False, synch_freq=0, verbose=False, use_streams=True,
+                 nprocs_per_node=1, local_node_group=None,
+                 transport='auto', compute_dtype=None, symmetric_world=None,
+                 heartbeat_timeout=HEARTBEAT_TIMEOUT, grid=None):
+        super(GossipDataParallel, self).__init__()
+        _INSTANCES[0] += 1
+        self._instance_id = _INSTANCES[0]
+        self._timeout_s = float(heartbeat_timeout)
+
+        first_param = next(module.parameters())
+        on_cuda = first_param.is_cuda
+        # one process per GPU: the default device list is the module's device,
+        # not "every visible GPU" (reference :49-52 drives 8 GPUs per process)
+        if device_ids is None:
+            device_ids = [first_param.device.index] if on_cuda else []
+        self.device_ids = list(device_ids)
+        self.output_device = self.device_ids[0] if self.device_ids else None
+        self.nprocs_per_node = nprocs_per_node
+
+        if world_size is None or rank is None:
+            assert dist.is_initialized()
+            rank, world_size = dist.get_rank(), dist.get_world_size()
+        self.process_rank = rank
+
+        self.local_node_group = local_node_group
+        if self.nprocs_per_node > 1:
+            self.local_rank = self.process_rank % self.nprocs_per_node
+            world_size //= nprocs_per_node
+            rank //= nprocs_per_node
+            if local_node_group is None:
+                for node in range(world_size):
+                    ranks = list(range(node * nprocs_per_node, (node + 1) * nprocs_per_node))
+                    grp = create_process_group(ranks)
+                    if self.process_rank in ranks:
+                        self.local_node_group = grp
+        else:
+            self.local_rank = 0
+        self.is_local_master = (self.process_rank % self.nprocs_per_node == 0)
+
+        self.module = module
+        self._module_copies = [self.module]
+        if len(self.device_ids) > 1:
+            self._init_multi_device()
+        first_param_dtype = first_param.dtype
+
+        # -- communication device / transport ------------------------------- #
+        backend_name = dist.get_backend() if dist.is_initialized() else None
+        if comm_device is None:
+            cpu_comm = (backend_name == 'gloo') or not on_cuda
+            comm_device = torch.device('cpu') if cpu_comm else torch.device('cuda', first_param.device.index)
+        comm_device = torch.device(comm_device)
+        if comm_device.type == 'cuda' and comm_device.index is None and on_cuda:
+            comm_device = torch.device('cuda', first_param.device.index)
+        self.__cpu_comm = comm_device.type == 'cpu'
+
+        if graph is None:
+            graph = NPDDEGraph(rank, world_size, self.nprocs_per_node, self.local_rank)
+        if mixing is None:
+            mixing = UniformMixing(graph, comm_device)
+
+        self.dist_config = {
+            'verbose': verbose, 'comm_device': comm_device, 'graph': graph,
+            'mixing': mixing, 'push_sum': push_sum, 'rank': rank,
+            'process_rank': self.process_rank, 'world_size': world_size,
+            'cpu_comm': self.__cpu_comm,
+        }
+        self.overlap = overlap
+        self.synch_freq = synch_freq
+        self.num_updates = 0
+        self.asynch = synch_freq > 0
+        self.logger = make_logger(rank, verbose)
+
+        # -- parameters -> flat arenas --------------------------------------- #
+        params = [p for p in module.parameters()]
+        by_dtype = group_by_dtype(params)
+        self._arenas: Dict[torch.dtype, FlatArena] = {}
+        for dtype, group in by_dtype.items():
+            arena = FlatArena(group, device=group[0].device)
+            arena.adopt(group)
+            self._arenas[dtype] = arena
+        self._params_by_dtype = by_dtype
+
+        all_fp32 = list(by_dtype.keys()) == [torch.float32]
+        if transport == 'auto':
+            use_kernels = on_cuda and not self.__cpu_comm and all_fp32 and _native_ok()
+        else:
+            use_kernels = transport in ('nvlink', 'kernel', 'peer')
+        if use_kernels and not (on_cuda and all_fp32):
+            raise RuntimeError('nvlink transport needs fp32 CUDA parameters')
+        if use_kernels and not _native_ok():
+            raise RuntimeError('nvlink transport requested but the sm_100a extension is '
+                               'not available (python -m stochastic_gradient_push_b200.ops.build)')
+
+        # push-sum weight (host mirror; the kernel transport keeps the truth on device)
+        self._ps_weight = torch.ones(1, device=comm_device, dtype=first_param_dtype)
+        self.is_ps_numerator = False
+        self.gossip_enable = True
+        self.gossiping = False
+        self.params_mixed = True
+        self.gossip_ps_factor = torch.zeros(1, device=comm_device, dtype=first_param_dtype)
+        self.gossip_ps_weight = self._ps_weight.clone()
+        self.lazy_mixing = (not self.asynch and mixing.is_regular() and not self.overlap)
+        self.lazy_ps_factor = self.gossip_ps_factor.clone()
+        self._w = 1.0                      # c10d transport: python mirror of ps_weight
+        self._fused_optimizer = None
+
+        if on_cuda and not self.__cpu_comm and use_streams:
+            self.gossip_stream = torch.cuda.Stream(device=first_param.device)
+        elif on_cuda:
+            self.gossip_stream = torch.cuda.current_stream(first_param.device)
+        else:
+            self.gossip_stream = None
+
+        # -- data plane ------------------------------------------------------- #
+        self._kernel = None
+        self._c10d = None
+        if self.is_local_master:
+            if use_kernels:
+                if symmetric_world is None:
+                    symmetric_world = self._make_symmetric_world(world_size, first_param.device)
+                self._kernel = _KernelBackend(
+                    self, self._arenas[torch.float32], graph, mixing, symmetric_world,
+                    overlap, compute_dtype, self._timeout_s, grid)
+            else:
+                self._c10d = _C10dBackend(self, self._arenas, graph, mixing, comm_device)
+        self.transport = 'nvlink' if self._kernel is not None else 'c10d'
+        self.dist_config['gossipers'] = {
+            dtype: _GossiperView(self, dtype) for dtype in self._arenas}
+        self.gossip_ps_factor.fill_(mixing.scalar_weights()[0])
+        self.lazy_ps_factor.copy_(self.gossip_ps_factor)
+        self.logger.debug('lazy mixing: {}; transport: {}'.format(self.lazy_mixing, self.transport))
+
+        self.__register_hooks()
+
+    # ------------------------------------------------------------------ #
+    # construction helpers
+    # ------------------------------------------------------------------ #
+    def _make_symmetric_world(self, world_size, device):
+        from .symmetric import LocalWorld, SymmetricWorld
+        if world_size == 1:
+            return LocalWorld(1, [device.index]).view(0)
+        group = None
+        if self.nprocs_per_node > 1:
+            masters = [r * self.nprocs_per_node for r in range(world_size)]
+            group = dist.new_group(masters)
+        return SymmetricWorld(device, group)
+
+    def _init_multi_device(self):
+        """Legacy single-process multi-GPU replicas (reference :87-99)."""
+        from torch.nn.parallel.replicate import replicate
+        self.broadcast_bucket_size = 10 * 1024 * 1024
+        self.nccl_reduce_bucket_size = 256 * 1024 * 1024
+        self._module_copies = replicate(self.module, self.device_ids, detach=True)
+        self._module_copies[0] = self.module
+        for cmodule in self._module_copies[1:]:
+            for p, cp in zip(self.module.parameters(), cmodule.parameters()):
+                cp.requires_grad = p.requires_grad
+
+    # ------------------------------------------------------------------ #
+    # properties
+    # ------------------------------------------------------------------ #
+    @property
+    def ps_weight(self):
+        if self._kernel is not None:
+            self._ps_weight.fill_(self._kernel.engine.ps_weight)
+        else:
+            self._ps_weight.fill_(self._w)
+        return self._ps_weight
+
+    @ps_weight.setter
+    def ps_weight(self, v):
+        val = float(v.reshape(-1)[0]) if torch.is_tensor(v) else float(v)
+        self._w = val
+        self._ps_weight.fill_(val)
+        if self._kernel is not None:
+            self._kernel.engine.ps_weight = val
+
+    @property
+    def arena(self) -> FlatArena:
+        """fp32 parameter arena (the flagship path)."""
+        return self._arenas[torch.float32]
+
+    @property
+    def engine(self):
+        return self._kernel.engine if self._kernel is not None else None
+
+    @property
+    def compute_shadow(self):
+        return self._kernel.shadow if self._kernel is not None else None
+
+    # ------------------------------------------------------------------ #
+    # reference API
+    # ------------------------------------------------------------------ #
+    def update_gossiper(self, attr, val):
+        """Set ``attr`` (in practice ``'peers_per_itr'``) on the gossipers."""
+        self.logger.debug('updating gossiper {} -> {}'.format(attr, val))
+        for gossiper in self.dist_config['gossipers'].values():
+            if val == getattr(gossiper, attr):
+                self.logger.debug('nothing to update')
+                return
+            setattr(gossiper, attr, val)
+
+    def state_dict(self, finish_gossip=True, *args, **kwargs):
+        if finish_gossip:
+            self._query_gossip_queue()
+            self._flush_pending()
+        super_dict = super(GossipDataParallel, self).state_dict(*args, **kwargs)
+        return {'state_dict': super_dict,
+                'ps_weight': self.ps_weight.detach().cpu().clone(),
+                'is_ps_numerator': self.is_ps_numerator}
+
+    def load_state_dict(self, load_dict, *args, **kwargs):
+        state_dict = load_dict['state_dict']
+        super(GossipDataParallel, self).load_state_dict(state_dict, *args, **kwargs)
+        self.ps_weight = load_dict['ps_weight']
+        self.is_ps_numerator = load_dict['is_ps_numerator']
+        if self._kernel is not None and self._kernel.shadow is not None:
+            self._kernel.shadow.copy_(self.arena.flat)
+
+    def forward(self, *inputs, **kwargs):
+        if self.device_ids:
+            inputs, kwargs = self.scatter(inputs, kwargs, self.device_ids)
+        else:
+            inputs, kwargs = (inputs,), (kwargs,)
+        if self.nprocs_per_node > 1:
+            self._sync_params_multiprocess()
+        if len(self.device_ids) > 1:
+            self._sync_params()
+            outputs = self.parallel_apply(self._module_copies[:len(inputs)], inputs, kwargs)
+            return self.gather(outputs, self.output_device)
+        return self.module(*inputs[0], **kwargs[0])
+
+    def scatter(self, inputs, kwargs, device_ids):
+        from torch.nn.parallel.scatter_gather import scatter_kwargs
+        return scatter_kwargs(inputs, kwargs, device_ids, dim=0)
+
+    def parallel_apply(self, replicas, inputs, kwargs):
+        from torch.nn.parallel.parallel_apply import parallel_apply
+        return parallel_apply(replicas, inputs, kwargs, self.device_ids[:len(replicas)])
+
+    def gather(self, outputs, output_device):
+        from torch.nn.parallel.scatter_gather import gather
+        return gather(outputs, output_device, dim=0)
+
+    def _sync_params(self):
+        """Intra-process replica sync (legacy multi-GPU, reference :256-276)."""
+        if len(self.device_ids) <= 1:
+            return
+        from torch.cuda.comm import broadcast_coalesced
+        for tensors_of in (self.module.parameters, self.module.buffers):
+            src = [t.data for t in tensors_of()]
+            if not src:
+                continue
+            result = broadcast_coalesced(src, self.device_ids, self.broadcast_bucket_size)
+            for tensors, mod in zip(result[1:], self._module_copies[1:]):
+                dst = mod.parameters() if tensors_of == self.module.parameters else mod.buffers()
+                for t, d in zip(tensors, dst):
+                    d.data.set_(t)
+
+    def _sync_params_multiprocess(self):
+        """Node master -> local ranks (reference :278-296); the parameters are
+        one flat arena per dtype so this is one broadcast per dtype."""
+        src = self.dist_config['rank'] * self.nprocs_per_node
+        for arena in self._arenas.values():
+            dist.broadcast(arena.flat, src=src, group=self.local_node_group)
+        buffers = [b.data for b in self.module.buffers()]
+        if buffers:
+            import functools
+            communicate(buffers, functools.partial(dist.broadcast, src=src,
+                                                   group=self.local_node_group))
+
+    # -- bias / de-bias ----------------------------------------------------- #
+    def ps_numerator(self):
+        """Convert the parameters to the push-sum numerator ``x = z * w``."""
+        if self.is_ps_numerator:
+            return
+        if self._kernel is not None and self._fused_optimizer is not None:
+            return      # the fused kernels re-bias internally; params stay de-biased
+        if not self.lazy_mixing:
+            self._scale_params(invert=False)
+        self.is_ps_numerator = True
+
+    def unbias(self):
+        """Convert the parameters to the de-biased estimate ``z = x / w``."""
+        if not self.is_ps_numerator:
+            return
+        if not self.lazy_mixing:
+            self._scale_params(invert=True)
+        self.is_ps_numerator = False
+
+    def _scale_params(self, invert):
+        if self._kernel is not None:
+            e = self._kernel.engine
+            e.C.scale_(e.z, e.ps_weight_tensor(), invert, e.shadow)
+        else:
+            w = self._w
+            if w == 1.0:
+                return
+            for arena in self._arenas.values():
+                arena.flat.mul_(1.0 / w if invert else w)
+
+    # -- train / eval -------------------------------------------------------- #
+    def train(self, mode=True):
+        super(GossipDataParallel, self).train(mode)
+        self.gossip_enable = True
+        for module in self._module_copies[1:]:
+            module.train(mode)
+        return self
+
+    def eval(self):
+        super(GossipDataParallel, self).eval()
+        # drain BEFORE disabling (the reference disables first, which turns its
+        # own drain into a no-op) so no peer message is lost
+        self._query_gossip_queue(non_blocking=self.asynch)
+        self._flush_pending()
+        self.gossip_enable = False
+        for module in self._module_copies[1:]:
+            module.eval()
+        return self
+
+    def block(self):
+        self.logger.info('blocking')
+        if dist.is_initialized():
+            dist.barrier()
+
+    def sync_comms(self):
+        self._query_gossip_queue(non_blocking=False)
+        self._flush_pending()
+
+    # -- gossip state machine ------------------------------------------------ #
+    def _query_gossip_queue(self, non_blocking=False):
+        """Fold the result of the in-flight gossip into the model.  Returns
+        True when something was folded, False otherwise."""
+        if not self.gossip_enable:
+            return
+        if not self.gossiping:
+            if self.is_local_master:
+                self.logger.debug('not gossiping right now')
+            return False
+
+        if self._kernel is not None:
+            k = self._kernel
+            if self.overlap and k.gather_event is not None:
+                if non_blocking and not k.gather_event.query():
+                    return False
+                torch.cuda.current_stream().wait_event(k.gather_event)
+                k.gather_event = None
+                k.residual_pending = True       # folded by the next publish / flush
+            # sync mode: the fused kernel already ran on this stream
+            self.params_mixed = True
+            self.gossiping = False
+            return True
+
+        c = self._c10d
+        if non_blocking and not c.done():
+            return False
+        self.ps_numerator()
+        self._w += c.finish()
+        self.params_mixed = True
+        self.gossiping = False
+        return True
+
+    def transfer_params(self, mix=True):
+        """Launch a gossip step with the current parameters."""
+        if not self.gossip_enable or not self.is_local_master:
+            return False
+        if not self.params_mixed:
+            self.logger.warning('params not mixed')
+            return False
+
+        if self._kernel is not None:
+            self._launch_kernel_gossip()
+        else:
+            self.ps_numerator()
+            c = self._c10d
+            self_w = c.start(self._w, pollable=self.asynch)
+            for arena in self._arenas.values():     # keep the self-loop share
+                arena.flat.mul_(self_w)
+            self._w *= self_w
+        self.params_mixed = False
+        self.gossiping = True
+        return True
+
+    def _launch_kernel_gossip(self):
+        k = self._kernel
+        e = k.engine
+        sgd = self._consume_pending_sgd()
+        in_numer = self.is_ps_numerator
+        if self.overlap:
+            e.publish(sgd=sgd, fold=k.residual_pending, in_numerator=in_numer)
+            k.residual_pending = False
+            cur = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.gossip_stream.wait_event(ev)
+            with torch.cuda.stream(self.gossip_stream):
+                e.gather()
+                k.gather_event = torch.cuda.Event()
+                k.gather_event.record(self.gossip_stream)
+        else:
+            e.mix(sgd=sgd, in_numerator=in_numer)
+        self.is_ps_numerator = False
+
+    def _consume_pending_sgd(self):
+        k = self._kernel
+        if k is not None and k.sgd_pending:
+            k.sgd_pending = False
+            return True
+        return False
+
+    def _flush_pending(self):
+        """Apply a deferred fused-SGD step and/or fold a gathered residual
+        without starting a new gossip (eval / checkpoint / sync_comms)."""
+        k = self._kernel
+        if k is None:
+            return
+        if k.sgd_pending or k.residual_pending or self.is_ps_numerator:
+            k.engine.local(sgd=self._consume_pending_sgd(), fold=k.residual_pending,
+                           in_numerator=self.is_ps_numerator)
+            k.residual_pending = False
+            self.is_ps_numerator = False
+
+    # -- hooks ----------------------------------------------------------------- #
+    def __register_hooks(self):
+        self.register_forward_pre_hook(self.__make_forward_pre_hook())
+        self.register_full_backward_pre_hook(self.__make_backward_hook())
+
+    def __make_backward_hook(self):
+        def hook(*unused):
+            if len(self.device_ids) > 1:
+                self._reduce_replica_grads()
+            if self.nprocs_per_node > 1:
+                grads = [p.grad.data for p in self.module.parameters()
+                         if p.requires_grad and p.grad is not None]
+                for g in grads:
+                    g.div_(self.nprocs_per_node)
+                import functools
+                communicate(grads, functools.partial(dist.all_reduce,
+                                                     group=self.local_node_group))
+            self.ps_numerator()
+
+        def queue_hook(*unused):
+            # run once, at the END of this backward pass (reference :567-569)
+            Variable._execution_engine.queue_callback(hook)
+        return queue_hook
+
+    def _reduce_replica_grads(self):
+        from torch.cuda.comm import reduce_add_coalesced
+        all_grads = [[] for _ in self._module_copies]
+        for dev_idx, module in enumerate(self._module_copies):
+            for p in module.parameters():
+                if p.requires_grad and p.grad is not None:
+                    all_grads[dev_idx].append(p.grad.data)
+        reduced = reduce_add_coalesced(all_grads, self.output_device,
+                                       self.nccl_reduce_bucket_size)
+        for grad, red in zip(all_grads[0], reduced):
+            grad.copy_(red)
+        for module in self._module_copies[1:]:
+            for param in module.parameters():
+                if param.requires_grad:
+                    param.grad = None
+
+    def __make_forward_pre_hook(self):
+        def hook(*unused):
+            if self.gossip_enable:
+                non_blocking = self.num_updates < self.synch_freq
+                if self._query_gossip_queue(non_blocking):
+                    self.num_updates = 0
+                else:
+                    self.num_updates += 1
+                if self.overlap:
+                    self.transfer_params()
+            if self._kernel is not None:
+                self._flush_pending()     # deferred SGD must land before forward
+            self.unbias()
+        return hook
+
+
+def _native_ok() -> bool:
+    from ..ops import native
+    return torch.cuda.is_available() and native.available()
+
+
+class _GossiperView(object):
+    """What ``dist_config['gossipers'][dtype]`` exposes: the knobs of the
+    reference's per-dtype gossiper (``peers_per_itr``, ``mixing_weights``,
+    ``ps_weight``) routed to whichever data plane is active."""
+
+    def __init__(self, owner: GossipDataParallel, dtype):
+        self._owner = owner
+        self.dtype = dtype
+
+    @property
+    def _graph(self):
+        return self._owner.dist_config['graph']
+
+    @property
+    def peers_per_itr(self):
+        return self._graph.peers_per_itr
+
+    @peers_per_itr.setter
+    def peers_per_itr(self, v):
+        o = self._owner
+        if v == self._graph.peers_per_itr:
+            return
+        # a schedule change is a global event: finish what is in flight first
+        o._query_gossip_queue(non_blocking=False)
+        o._flush_pending()
+        if o._kernel is not None:
+            torch.cuda.synchronize()
+            o._kernel.engine.sync_graph()
+        if dist.is_initialized():
+            dist.barrier()
+        self._graph.peers_per_itr = v
+        if o._kernel is not None:
+            o._kernel.engine.set_schedule(self._graph, o.dist_config['mixing'])
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()
+        o.gossip_ps_factor.fill_(o.dist_config['mixing'].scalar_weights()[0])
+
+    @property
+    def mixing_weights(self):
+        return self._owner.dist_config['mixing'].get_mixing_weights()
+
+    @property
+    def ps_weight(self):
+        return self._owner.ps_weight
+
+    @property
+    def regular(self):
+        return self._owner.dist_config['mixing'].is_regular()

@@ -39,6 +39,11 @@ class FlatArena(object):
         self.device = torch.device(device) if device is not None else tensors[0].device
         self.shapes = [tuple(t.shape) for t in tensors]
         self.numels = [t.numel() for t in tensors]
+        # 4-D tensors already stored channels-last keep that layout inside the
+        # arena (cuDNN NHWC kernels then read the weights without a transpose)
+        self.channels_last = [
+            t.dim() == 4 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last) for t in tensors]
         self.offsets: List[int] = []
         off = 0
         for n in self.numels:
@@ -66,8 +71,15 @@ class FlatArena(object):
     def views_of(self, flat: torch.Tensor) -> List[torch.Tensor]:
         """Per-tensor views of any buffer that shares this layout."""
         assert flat.numel() >= self.used
-        return [flat.narrow(0, o, n).view(s)
-                for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        out = []
+        for o, n, s, cl in zip(self.offsets, self.numels, self.shapes, self.channels_last):
+            v = flat.narrow(0, o, n)
+            if cl:      # (N,C,H,W) logical shape over an (N,H,W,C) physical layout
+                v = v.view(s[0], s[2], s[3], s[1]).permute(0, 3, 1, 2)
+            else:
+                v = v.view(s)
+            out.append(v)
+        return out
 
     def new_buffer(self, dtype=None, allocator=None, zero=True) -> torch.Tensor:
         """Another flat buffer with the same layout (grads, momentum, shadow)."""
@@ -82,7 +94,7 @@ class FlatArena(object):
     def adopt(self, params: Iterable[torch.Tensor]):
         """Copy the current values in and re-point ``p.data`` at the views."""
         for p, v in zip(params, self.views):
-            v.copy_(p.detach().to(v.device, v.dtype).reshape(v.shape))
+            v.copy_(p.detach().to(v.device, v.dtype))
             p.data = v
 
     @torch.no_grad()
@@ -98,5 +110,5 @@ class FlatArena(object):
         layout -- the slow path used only for foreign tensors."""
         out = self.new_buffer() if out is None else out
         for t, v in zip(tensors, self.views_of(out)):
-            v.copy_(t.reshape(v.shape))
+            v.copy_(t.view(v.shape) if t.shape != v.shape else t)
         return out

@@ -1,0 +1,192 @@
+"""GossipDataParallel over the c10d (gloo, CPU) transport vs a single-process
+simulation of the whole world (SURVEY 4.2 'Dist-CPU' tier)."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+import stochastic_gradient_push_b200 as sgp
+from stochastic_gradient_push_b200.ops import oracle
+
+from dist_utils import run_distributed
+
+LR, MU, WD = 0.05, 0.9, 1e-3
+
+
+def _model(seed):
+    torch.manual_seed(seed)
+    return nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3))
+
+
+def _batch(rank, step):
+    g = torch.Generator().manual_seed(1000 * rank + step)
+    return torch.randn(4, 6, generator=g), torch.randn(4, 3, generator=g)
+
+
+def _flat(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, nesterov):
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    graph = getattr(sgp, graph_name)(rank, world, peers_per_itr=ppi)
+    model = GossipDataParallel(_model(rank), graph=graph, push_sum=push_sum, overlap=overlap,
+                               rank=rank, world_size=world, verbose=False)
+    assert model.transport == 'c10d'
+    if fused:
+        opt = FusedGossipSGD(model, lr=LR, momentum=MU, weight_decay=WD, nesterov=nesterov)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=LR, momentum=MU, weight_decay=WD,
+                              nesterov=nesterov)
+    model.train()
+    for step in range(steps):
+        x, y = _batch(rank, step)
+        loss = ((model(x) - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if not overlap:
+            model.transfer_params()
+    model.sync_comms()
+    model.unbias()
+    sd = model.state_dict()
+    return _flat(model.module).tolist(), float(sd['ps_weight']), sd['is_ps_numerator']
+
+
+def _simulate(world, graph_name, ppi, steps, overlap, nesterov):
+    """All ranks in one process, plain tensors, straight from the algebra in
+    SURVEY 3.3/3.4."""
+    models = [_model(r) for r in range(world)]
+    graphs = [getattr(sgp, graph_name)(r, world, peers_per_itr=ppi) for r in range(world)]
+    mix = [sgp.UniformMixing(g, 'cpu') for g in graphs]
+    ws = [1.0] * world
+    moms = [torch.zeros_like(_flat(m)) for m in models]
+    xs = [_flat(m).clone() for m in models]          # numerators
+    res = [torch.zeros_like(x) for x in xs]
+    wres = [0.0] * world
+
+    def load(m, flat):
+        off = 0
+        for p in m.parameters():
+            n = p.numel()
+            p.data.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    for step in range(steps):
+        if overlap:
+            # pre-forward: fold residual, pre-scale, snapshot & send
+            xs = [x + r for x, r in zip(xs, res)]
+            ws = [w + wr for w, wr in zip(ws, wres)]
+            cols = [mix[j].scalar_weights(graphs[j].get_peers()[0]) for j in range(world)]
+            snap, snapw = [x.clone() for x in xs], list(ws)
+            for i in range(world):
+                _, ins = graphs[i].get_peers()
+                res[i] = sum(cols[j][1][i] * snap[j] for j in ins)
+                wres[i] = sum(cols[j][1][i] * snapw[j] for j in ins)
+                xs[i] = cols[i][0] * xs[i]
+                ws[i] = cols[i][0] * ws[i]
+            oracle.rotate_all(graphs)
+        grads = []
+        for i, m in enumerate(models):
+            load(m, xs[i] / ws[i])
+            m.zero_grad()
+            x, y = _batch(i, step)
+            ((m(x) - y) ** 2).mean().backward()
+            grads.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+        for i in range(world):
+            xs[i], moms[i] = oracle.sgd_momentum(xs[i], grads[i], moms[i], LR, MU, WD, nesterov)
+        if not overlap:
+            xs, ws = oracle.mix_columns(xs, ws, graphs, mix)
+            oracle.rotate_all(graphs)
+    if overlap:
+        xs = [x + r for x, r in zip(xs, res)]
+        ws = [w + wr for w, wr in zip(ws, wres)]
+    return [x / w for x, w in zip(xs, ws)], ws
+
+
+@pytest.mark.parametrize('graph_name,ppi,push_sum,fused,nesterov', [
+    ('NPeerDynamicDirectedExponentialGraph', 1, True, False, True),
+    ('NPeerDynamicDirectedExponentialGraph', 1, True, True, True),
+    ('DynamicDirectedExponentialGraph', 2, True, True, False),
+    ('RingGraph', 1, False, False, False),
+    ('DynamicBipartiteExponentialGraph', 1, False, True, True),
+])
+def test_sync_gossip_matches_simulation(graph_name, ppi, push_sum, fused, nesterov):
+    world, steps = 4, 5
+    out = run_distributed(_worker, world, graph_name, ppi, steps, push_sum, False, fused, nesterov)
+    want, ws = _simulate(world, graph_name, ppi, steps, False, nesterov)
+    for r in range(world):
+        got, w, is_num = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5 and is_num is False
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_overlap_adds_residual_one_step_late(fused):
+    world, steps = 4, 5
+    out = run_distributed(_worker, world, 'NPeerDynamicDirectedExponentialGraph', 1, steps,
+                          True, True, fused, False)
+    want, ws = _simulate(world, 'NPeerDynamicDirectedExponentialGraph', 1, steps, True, False)
+    for r in range(world):
+        got, w, _ = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5
+
+
+def _state_roundtrip(rank, world):
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    graph = sgp.RingGraph(rank, world)
+    model = GossipDataParallel(_model(rank), graph=graph, rank=rank, world_size=world)
+    model.ps_weight = 0.75
+    sd = model.state_dict()
+    assert set(sd) == {'state_dict', 'ps_weight', 'is_ps_numerator'}
+    assert all(k.startswith('module.') for k in sd['state_dict'])
+    other = GossipDataParallel(_model(99), graph=sgp.RingGraph(rank, world), rank=rank,
+                               world_size=world)
+    other.load_state_dict(copy.deepcopy(sd))
+    assert abs(float(other.ps_weight) - 0.75) < 1e-7
+    assert torch.equal(_flat(other.module), _flat(model.module))
+    # parameters are views of one arena
+    arena = other.arena
+    p0 = next(other.module.parameters())
+    assert p0.data_ptr() == arena.flat.data_ptr()
+    # transfer_params refuses while the previous gossip is un-mixed
+    assert model.transfer_params() is True
+    assert model.transfer_params() is False
+    model.sync_comms()
+    assert model.params_mixed and not model.gossiping
+    # eval drains and disables, train re-enables
+    model.eval()
+    assert model.gossip_enable is False and model.transfer_params() is False
+    model.train()
+    assert model.gossip_enable is True
+    return True
+
+
+def test_state_dict_and_flags():
+    assert all(run_distributed(_state_roundtrip, 2))
+
+
+def _ppi_update(rank, world):
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    graph = sgp.DynamicDirectedExponentialGraph(rank, world)
+    model = GossipDataParallel(_model(rank), graph=graph, rank=rank, world_size=world)
+    model.transfer_params()
+    model.update_gossiper('peers_per_itr', 2)
+    assert graph.peers_per_itr == 2 and graph._group_indices == [0, 1]
+    model.update_gossiper('peers_per_itr', 2)      # no-op second time
+    for _ in range(6):
+        model.transfer_params()
+        model.sync_comms()
+    model.unbias()
+    return _flat(model.module).tolist()
+
+
+def test_update_gossiper_peers_per_itr_and_consensus():
+    world = 4
+    out = run_distributed(_ppi_update, world)
+    mean = sum(_flat(_model(r)) for r in range(world)) / world
+    for r in range(world):
+        torch.testing.assert_close(torch.tensor(out[r]), mean, rtol=0, atol=2e-3)

@@ -116,10 +116,12 @@ def test_mix_reaches_exact_mean_npdde8():
 
 def test_irregular_mixing_tracks_push_sum_weight():
     n, numel, steps = 4, 2 * CHUNK, 9
+    import functools
+    mix_cls = functools.partial(sgp.SelfWeightedMixing, self_weight=[0.3, 0.5, 0.6, 0.45])
     engines, graphs, _, streams = _mk_world(
         n, numel, sgp.DynamicDirectedExponentialGraph, 1,
-        mixing_cls=sgp.SelfWeightedMixing, with_sgd=False)
-    ogs, oms = _oracle_graphs(graphs, sgp.SelfWeightedMixing)
+        mixing_cls=mix_cls, with_sgd=False)
+    ogs, oms = _oracle_graphs(graphs, mix_cls)
     xs = [e.z.double().clone() for e in engines]
     total = sum(xs)
     ws = [1.0] * n
