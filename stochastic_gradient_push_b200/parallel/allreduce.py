@@ -1,0 +1,177 @@
+"""
+AllReduce-SGD comparator.
+
+The reference's AR baseline is ``torch.nn.parallel.DistributedDataParallel``
+(``gossip_sgd.py:179-180``): bucketed NCCL all-reduces + a separate optimizer.
+Here the exact-averaging baseline is built from the same parts as the gossip
+path so the comparison isolates the algorithm:
+
+* parameters in one flat arena, gradients in ONE flat buffer that lives in
+  NVSwitch-mapped symmetric memory;
+* ``sgp_allreduce_sgd_kernel``: every rank pulls all peers' gradient buffers
+  with 16-byte P2P loads, sums them in rank order (replicas stay bit-identical),
+  scales by 1/world and applies SGD-momentum in the same pass -- one kernel,
+  no NCCL call, no bucket copies;
+* ``transport='nccl'`` keeps a library path (one in-place ``all_reduce`` on the
+  flat gradient + the fused local SGD kernel) as a second comparator.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch.nn.modules import Module
+
+from ..ops import native
+from ..utils.arena import FlatArena
+from .trainer import GossipTrainer
+
+
+class AllReduceDataParallel(Module):
+
+    def __init__(self, module, rank=None, world_size=None, transport='p2p',
+                 grad_dtype=torch.float32, timeout_s=60.0, grid=None):
+        super().__init__()
+        self.module = module
+        if rank is None or world_size is None:
+            if dist.is_initialized():
+                rank, world_size = dist.get_rank(), dist.get_world_size()
+            else:
+                rank, world_size = 0, 1
+        self.rank, self.world_size = rank, world_size
+        self.transport = transport
+        params = list(module.parameters())
+        assert all(p.dtype == torch.float32 and p.is_cuda for p in params)
+        self.device = params[0].device
+        self.arena = FlatArena(params, device=self.device)
+        self.arena.adopt(params)
+        if world_size > 1:          # AR replicas must start identical
+            dist.broadcast(self.arena.flat, src=0)
+            for b in module.buffers():
+                dist.broadcast(b.data, src=0)
+        C = native.load()
+        self.C = C
+        from .symmetric import LocalWorld, SymmetricWorld
+        self.world = (SymmetricWorld(self.device) if world_size > 1
+                      else LocalWorld(1, [self.device.index]).view(0))
+        n = self.arena.total
+        esize = 4 if grad_dtype == torch.float32 else 2
+        self._grad_buf = self.world.alloc('ar.grad', n * esize)
+        self.grad_flat = self._grad_buf.local.view(grad_dtype)[:n]
+        self.grad_flat.zero_()
+        self.arena.bind_grads(params, self.grad_flat)
+        self.momentum = self.arena.new_buffer()
+        self.pad = self.world.alloc('ar.pad', C.PAD_BYTES)
+        self.state = torch.zeros(C.STATE_BYTES, dtype=torch.uint8, device=self.device)
+        self.state.view(torch.float32)[C.STATE_OFF_PSW // 4: C.STATE_OFF_PSW // 4 + 2] = 1.0
+        self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32).pin_memory()
+        self._hyper_cache = None
+        table = torch.zeros(1, C.TABLE_ROW, dtype=torch.int32, device=self.device)
+        wtable = torch.zeros(1, C.WTABLE_ROW, dtype=torch.float32, device=self.device)
+        wtable[0, 0] = 1.0
+        self.ctx = C.GossipContext(
+            z=self.arena.flat, g=self.grad_flat, m=self.momentum, shadow=None, residual=None,
+            pad_ptrs=self.pad.table, outbox_ptrs=None, table=table, wtable=wtable,
+            rank=self.world.rank, world=self.world.world, state=self.state, hyper=self.hyper,
+            timeout_s=float(timeout_s))
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        if grid is None:
+            grid = min(self.ctx.max_grid(), 2 * sms)
+        self.grid = int(max(1, min(grid, n // C.CHUNK)))
+        self.steps = 0
+        torch.cuda.synchronize(self.device)
+        self.world.barrier()
+
+    def forward(self, *a, **kw):
+        return self.module(*a, **kw)
+
+    def set_hyper(self, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
+        key = (float(lr), float(momentum), float(weight_decay), bool(nesterov), float(grad_scale))
+        if key == self._hyper_cache:
+            return
+        self._hyper_cache = key
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4], h[5] = key[0], key[1], key[2], float(key[3]), 1.0, key[4]
+        self.hyper.copy_(h, non_blocking=True)
+
+    def allreduce_step(self):
+        """grads <- mean over ranks ; SGD-momentum ; grads <- 0   (current stream)"""
+        C = self.C
+        if self.transport == 'nccl' and self.world_size > 1:
+            dist.all_reduce(self.grad_flat)
+            self.set_hyper(*self._hyper_cache[:4], grad_scale=1.0 / self.world_size)
+            self.ctx.step(C.F_SGD | C.F_ZERO_GRAD | C.F_PHASE1 | C.F_NO_ROTATE, self.grid)
+        else:
+            self.ctx.allreduce_sgd(self._grad_buf.table, 0, self.grid)
+            C.zero_(self.grad_flat)
+            self.steps += 1
+
+    def check(self):
+        st = int(self.state.view(torch.int32)[self.C.STATE_OFF_STATUS // 4].item())
+        if st != 0:
+            raise RuntimeError('all-reduce kernel error %d on rank %d' % (st, self.rank))
+
+
+class _EngineShim(object):
+    """The slice of GossipEngine that GossipTrainer touches."""
+
+    def __init__(self, ar: AllReduceDataParallel):
+        self.ar = ar
+        self.device = ar.device
+        self.steps = 0
+
+    def set_hyper(self, lr, momentum, weight_decay, nesterov, do_sgd=True, grad_scale=1.0):
+        self.ar.set_hyper(lr, momentum, weight_decay, nesterov, grad_scale)
+
+    def check(self):
+        self.ar.check()
+
+
+class ARTrainer(GossipTrainer):
+    """Graph-captured forward/backward + the fused all-reduce+SGD kernel."""
+
+    def __init__(self, model: AllReduceDataParallel, lr, momentum=0.9, weight_decay=1e-4,
+                 nesterov=True, criterion=None, amp_dtype=torch.bfloat16, use_cuda_graph=True,
+                 warmup_iters=3, channels_last=True):
+        self.model = model
+        self.ar = model
+
+        class _Opt(object):
+            param_groups = [dict(lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                 nesterov=nesterov)]
+            grad_scale = 1.0
+        self.opt = _Opt()
+        self.engine = _EngineShim(model)
+        self.k = None
+        self.criterion = criterion or torch.nn.CrossEntropyLoss()
+        self.amp_dtype = amp_dtype
+        self.use_graph = use_cuda_graph
+        self.warmup_iters = warmup_iters
+        self.channels_last = channels_last
+        self.device = model.device
+        self.overlap = False
+        self.gossip = False
+        self.graph = None
+        self.static_in = self.static_tgt = self.static_loss = self.static_out = None
+        self._eager_steps = 0
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage = self._stage_tgt = None
+        self._stage_ready = torch.cuda.Event()
+        self._stage_free = torch.cuda.Event()
+        self._prefetched = False
+        self._loss_ring = None
+        self._loss_slot = 0
+
+    def _one_step(self, first=False):
+        self._fwd_bwd()
+        self.ar.allreduce_step()
+
+    def _after_replay(self):
+        self.ar.steps += 1
+
+    def finish(self):
+        torch.cuda.synchronize(self.device)
+        self.ar.check()

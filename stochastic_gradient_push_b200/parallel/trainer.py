@@ -1,0 +1,230 @@
+"""
+GossipTrainer: the flagship training step, captured ONCE as a CUDA graph.
+
+One replay = forward (bf16 autocast, NHWC) + loss + backward + ONE fused
+gossip kernel (SGD-momentum + publish + P2P pull + mix + de-bias), i.e. the
+reference's whole hot loop (``gossip_sgd.py:369-393`` + the pre-forward /
+backward hooks + the gossip thread) with zero Python on the critical path:
+
+* the time-varying graph is a device table the kernel indexes with its own
+  device-side step counter; the learning rate lives in device memory -- so the
+  captured graph never needs re-capturing;
+* Overlap-SGP forks the gather kernel onto ``gossip_stream`` INSIDE the graph:
+  it pulls the peers' parameters over NVLink while forward/backward run;
+* inputs arrive from pinned host memory through a prefetch stream (H2D of step
+  k+1 overlaps compute of step k); the loss is read back through a pinned ring
+  without a per-step host synchronisation.
+
+Modes: ``'sgp'`` (push-sum, directed graph), ``'dpsgd'`` (push-pull, symmetric
+graph) -- same kernel, the graph/mixing differ --, ``'osgp'`` (overlap), and
+``'local'`` (world size 1 / gossip disabled).
+"""
+
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, Optional
+
+import torch
+
+from ..optim import FusedGossipSGD
+from .distributed import GossipDataParallel
+
+
+class GossipTrainer(object):
+
+    def __init__(self, model: GossipDataParallel, optimizer: FusedGossipSGD,
+                 criterion: Optional[Callable] = None, amp_dtype=torch.bfloat16,
+                 use_cuda_graph: bool = True, warmup_iters: int = 3,
+                 channels_last: bool = True):
+        assert model._kernel is not None, 'GossipTrainer drives the nvlink kernel transport'
+        self.model = model
+        self.opt = optimizer
+        self.engine = model._kernel.engine
+        self.k = model._kernel
+        self.criterion = criterion or torch.nn.CrossEntropyLoss()
+        self.amp_dtype = amp_dtype
+        self.use_graph = use_cuda_graph
+        self.warmup_iters = warmup_iters
+        self.channels_last = channels_last
+        self.device = self.engine.device
+        self.overlap = model.overlap
+        self.gossip = model.dist_config['world_size'] > 1
+        self.graph = None
+        self.static_in = None
+        self.static_tgt = None
+        self.static_loss = None
+        self.static_out = None
+        self._eager_steps = 0
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage = None
+        self._stage_tgt = None
+        self._stage_ready = torch.cuda.Event()
+        self._stage_free = torch.cuda.Event()
+        self._prefetched = False
+        self._loss_ring = None
+        self._loss_slot = 0
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------ #
+    def _autocast(self):
+        if self.amp_dtype is None or self.amp_dtype == torch.float32:
+            return contextlib.nullcontext()
+        return torch.autocast('cuda', dtype=self.amp_dtype)
+
+    def _fwd_bwd(self):
+        with self._autocast():
+            out = self.model.module(self.static_in)
+            loss = self.criterion(out.float(), self.static_tgt)
+        loss.backward()
+        self.static_loss.copy_(loss.detach())
+        self.static_out = out
+
+    def _gossip_kernels(self, first: bool):
+        """The gossip / optimizer launches of one step.  ``first``: no gradient
+        and no residual exist yet (only relevant for overlap)."""
+        e = self.engine
+        if not self.gossip or not self.model.gossip_enable:
+            e.local(sgd=True)
+        elif self.overlap:
+            raise RuntimeError('overlap handled in _step_overlap')
+        else:
+            e.mix(sgd=True)
+
+    def _step_sync(self):
+        self._fwd_bwd()
+        self._gossip_kernels(False)
+
+    def _step_overlap(self, first: bool):
+        """publish(k) -> [gather(k) on gossip_stream || fwd/bwd(k)] ; the SGD of
+        step k is fused into publish(k+1)."""
+        e, k = self.engine, self.k
+        main = torch.cuda.current_stream(self.device)
+        side = self.model.gossip_stream
+        e.publish(sgd=not first, fold=not first)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            e.gather()
+            join = torch.cuda.Event()
+            join.record(side)
+        self._fwd_bwd()
+        main.wait_event(join)
+
+    def _one_step(self, first=False):
+        if self.overlap and self.gossip and self.model.gossip_enable:
+            self._step_overlap(first)
+        else:
+            self._step_sync()
+
+    # ------------------------------------------------------------------ #
+    def _ensure_static(self, batch, target):
+        if self.static_in is not None:
+            return
+        fmt = torch.channels_last if (self.channels_last and batch.dim() == 4) \
+            else torch.contiguous_format
+        self.static_in = torch.empty(batch.shape, dtype=batch.dtype, device=self.device
+                                     ).contiguous(memory_format=fmt)
+        self.static_tgt = torch.empty(target.shape, dtype=target.dtype, device=self.device)
+        # staging keeps the HOST layout (plain pinned memcpy); the device-side
+        # stage -> static copy performs the NCHW -> NHWC permute
+        self._stage = torch.empty(batch.shape, dtype=batch.dtype, device=self.device)
+        self._stage_tgt = torch.empty_like(self.static_tgt)
+        self.static_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._loss_ring = torch.zeros(1024, dtype=torch.float32).pin_memory()
+        self._stage_free.record(torch.cuda.current_stream(self.device))
+
+    def _set_lr(self):
+        g = self.opt.param_groups[0]
+        self.engine.set_hyper(g['lr'], g['momentum'], g['weight_decay'], g['nesterov'],
+                              do_sgd=True, grad_scale=self.opt.grad_scale)
+
+    def prefetch(self, batch_cpu, target_cpu):
+        """Start the H2D copy of the NEXT step's inputs on the copy stream."""
+        self._ensure_static(batch_cpu, target_cpu)
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)
+        with torch.cuda.stream(cs):
+            self._stage.copy_(batch_cpu, non_blocking=True)
+            self._stage_tgt.copy_(target_cpu, non_blocking=True)
+            self._stage_ready.record(cs)
+        self._prefetched = True
+
+    def _load_inputs(self, batch, target):
+        main = torch.cuda.current_stream(self.device)
+        if batch is not None and not self._prefetched:
+            self.prefetch(batch, target)
+        main.wait_event(self._stage_ready)
+        self.static_in.copy_(self._stage, non_blocking=True)
+        self.static_tgt.copy_(self._stage_tgt, non_blocking=True)
+        self._stage_free.record(main)
+        self._prefetched = False
+
+    def step(self, batch=None, target=None, next_batch=None, next_target=None,
+             read_loss: bool = True):
+        """One training iteration through the public path.
+
+        ``batch``/``target``: (pinned) host or device tensors for THIS step;
+        pass ``None`` if a previous call already staged them via
+        ``next_batch``/``prefetch``.  ``next_batch``/``next_target``: inputs of
+        the FOLLOWING step; their H2D copy is started on the prefetch stream as
+        soon as this step's inputs have left the staging buffer, so it overlaps
+        this step's compute.  Returns the slot of :attr:`loss_ring` that holds
+        this step's loss once the stream has drained (no host sync here)."""
+        if batch is not None:
+            self._ensure_static(batch, target)
+        self._load_inputs(batch, target)
+        if next_batch is not None:
+            self.prefetch(next_batch, next_target)
+        self._run()
+        slot = self._loss_slot
+        if read_loss:
+            self._loss_ring[slot:slot + 1].copy_(self.static_loss.view(1), non_blocking=True)
+            self._loss_slot = (slot + 1) % self._loss_ring.numel()
+        return slot
+
+    def step_resident(self):
+        """Replay the step on whatever is resident in the static input buffers
+        (no H2D, no loss read-back): the device-only number of bench.py."""
+        assert self.static_in is not None
+        self._run()
+
+    def _run(self):
+        self._set_lr()
+        e = self.engine
+        if self.graph is not None:
+            self.graph.replay()
+            self._after_replay()
+        elif self.use_graph and self._eager_steps >= self.warmup_iters:
+            self._capture()
+            self.graph.replay()
+            self._after_replay()
+        else:
+            self._one_step(first=(self._eager_steps == 0))
+            self._eager_steps += 1
+
+    def _after_replay(self):
+        if self.gossip and self.model.gossip_enable:
+            self.engine.steps += 1
+
+    @property
+    def loss_ring(self):
+        return self._loss_ring
+
+    def _capture(self):
+        torch.cuda.synchronize(self.device)
+        steps_before = self.engine.steps
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+            self._one_step(first=False)
+        # capture does not execute: undo the host-side step mirror advance
+        self.engine.steps = steps_before
+        torch.cuda.synchronize(self.device)
+
+    def finish(self):
+        """Drain: apply the last deferred SGD / residual (overlap) and sync."""
+        if self.overlap and self.gossip:
+            self.engine.local(sgd=True, fold=True)
+        torch.cuda.synchronize(self.device)
+        self.engine.check()

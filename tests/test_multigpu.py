@@ -99,3 +99,98 @@ def test_random_skew_conserves_mass():
     out = run_distributed(_skew_worker, n, 40, backend='nccl', timeout=300)
     mean = sum(range(n)) / n
     assert all(abs(v - mean) < 1e-3 for v in out)         # 40 steps >> log2(n): consensus
+
+
+# --------------------------------------------------------------------------- #
+# GossipDataParallel on the nvlink kernel transport vs the world simulation
+# --------------------------------------------------------------------------- #
+def _gdp_worker(rank, world, graph_name, ppi, steps, overlap, fused, nesterov):
+    import test_distributed_c10d as sim
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    dev = torch.device('cuda', rank)
+    graph = getattr(sgp, graph_name)(rank, world, peers_per_itr=ppi)
+    net = sim._model(rank).to(dev)
+    model = GossipDataParallel(net, graph=graph, overlap=overlap, rank=rank, world_size=world,
+                               heartbeat_timeout=20)
+    assert model.transport == 'nvlink'
+    if fused:
+        opt = FusedGossipSGD(model, lr=sim.LR, momentum=sim.MU, weight_decay=sim.WD,
+                             nesterov=nesterov)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=sim.LR, momentum=sim.MU,
+                              weight_decay=sim.WD, nesterov=nesterov)
+    model.train()
+    for step in range(steps):
+        x, y = sim._batch(rank, step)
+        loss = ((model(x.to(dev)) - y.to(dev)) ** 2).mean()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if not overlap:
+            model.transfer_params()
+    model.sync_comms()
+    model.unbias()
+    torch.cuda.synchronize()
+    model.engine.check()
+    return sim._flat(model.module).cpu().tolist(), float(model.ps_weight)
+
+
+@pytest.mark.parametrize('graph_name,ppi,overlap,fused,nesterov', [
+    ('NPeerDynamicDirectedExponentialGraph', 1, False, True, True),
+    ('NPeerDynamicDirectedExponentialGraph', 1, False, False, True),
+    ('DynamicDirectedExponentialGraph', 2, False, True, False),
+    ('NPeerDynamicDirectedExponentialGraph', 1, True, True, False),
+    ('NPeerDynamicDirectedExponentialGraph', 1, True, False, False),
+    ('RingGraph', 1, False, True, True),
+])
+def test_gossip_data_parallel_kernels_match_simulation(graph_name, ppi, overlap, fused, nesterov):
+    import test_distributed_c10d as sim
+    n = min(_ngpu(), 4)
+    n = n if n % 2 == 0 else n - 1
+    steps = 5
+    out = run_distributed(_gdp_worker, n, graph_name, ppi, steps, overlap, fused, nesterov,
+                          backend='nccl', timeout=300)
+    want, ws = sim._simulate(n, graph_name, ppi, steps, overlap, nesterov)
+    for r in range(n):
+        got, w = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5
+
+
+def _trainer_worker(rank, world, algo, use_graph, steps):
+    from stochastic_gradient_push_b200 import models
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(7 + rank)
+    net = models.TinyConvNet().to(dev).to(memory_format=torch.channels_last)
+    graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world)
+    model = GossipDataParallel(net, graph=graph, overlap=(algo == 'osgp'), rank=rank,
+                               world_size=world, heartbeat_timeout=20)
+    opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    tr = GossipTrainer(model, opt, amp_dtype=None, use_cuda_graph=use_graph, warmup_iters=2)
+    g = torch.Generator().manual_seed(100 + rank)
+    losses = []
+    for s in range(steps):
+        x = torch.randn(8, 3, 32, 32, generator=g).pin_memory()
+        y = torch.randint(0, 10, (8,), generator=g).pin_memory()
+        slot = tr.step(x, y)
+        torch.cuda.synchronize()
+        losses.append(float(tr.loss_ring[slot]))
+    tr.finish()
+    return model.arena.flat.cpu().tolist(), losses, model.engine.device_step
+
+
+@pytest.mark.parametrize('algo', ['sgp', 'osgp'])
+def test_graphed_trainer_equals_eager(algo):
+    n = 2
+    steps = 7
+    eager = run_distributed(_trainer_worker, n, algo, False, steps, backend='nccl', timeout=300)
+    graphed = run_distributed(_trainer_worker, n, algo, True, steps, backend='nccl', timeout=300)
+    for r in range(n):
+        torch.testing.assert_close(torch.tensor(graphed[r][0]), torch.tensor(eager[r][0]),
+                                   rtol=1e-4, atol=1e-5)
+        assert graphed[r][2] == eager[r][2] == steps
+        assert all(l == l for l in graphed[r][1])
