@@ -18,6 +18,7 @@ The only substitutions are the ones SURVEY.md 7.4 lists as unavoidable:
   batch W and batch W+K are requested, so exactly K iterations of the stock
   loop are timed, end to end (H2D of the batch, fwd/bwd, optimizer.step,
   transfer_params, the loop's own accuracy/.item() reads).
+* ``accuracy()`` gets a one-word torch>=1.7 fix (``.view`` -> ``.reshape``);
 * world size 1: gossip graphs are undefined for n=1 in the reference (math
   domain error in ``graph_manager``), so N=1 runs its AllReduce-SGD path
   (``--all_reduce True``, DistributedDataParallel); DDP without ``device_ids``
@@ -159,6 +160,24 @@ def main(args):
         return []          # --train_fast: one (empty) validation pass at the end
 
     ref.make_dataloader = make_dataloader
+
+    # torch >= 1.7 compatibility: the reference's accuracy() calls .view(-1) on a
+    # non-contiguous slice (gossip_sgd.py:486) and raises; same maths with
+    # .reshape(-1), as upstream pytorch/examples fixed it.
+    def accuracy(output, target, topk=(1,)):
+        with torch.no_grad():
+            maxk = max(topk)
+            batch_size = target.size(0)
+            _, pred = output.topk(maxk, 1, True, True)
+            pred = pred.t()
+            correct = pred.eq(target.view(1, -1).expand_as(pred))
+            res = []
+            for k in topk:
+                correct_k = correct[:k].reshape(-1).float().sum(0, keepdim=True)
+                res.append(correct_k.mul_(100.0 / batch_size))
+            return res
+
+    ref.accuracy = accuracy
     t_all = time.time()
     ref.main()
     torch.cuda.synchronize()

@@ -185,10 +185,10 @@ def run_ours(args):
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    e0.record()
+    e0.record(trainer.stream)
     for i in range(K):
         trainer.step_resident()
-    e1.record()
+    e1.record(trainer.stream)
     sync_all()
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -202,12 +202,12 @@ def run_ours(args):
     if not args.skip_e2e:
         trainer.prefetch(*pool[0])
         sync_all()
-        e0.record()
+        e0.record(trainer.stream)
         slots = []
         for i in range(K):
             nxt = pool[(i + 1) % len(pool)]
             slots.append(trainer.step(None, None, nxt[0], nxt[1]))
-        e1.record()
+        e1.record(trainer.stream)
         sync_all()
         losses = [float(trainer.loss_ring[s]) for s in slots]     # D2H results, all K read
         ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -4,6 +4,11 @@ the B200 execution model: NHWC (channels_last) activations and weights, bf16
 tensor-core math under autocast with fp32 master weights in the gossip arena,
 BatchNorm statistics and affine parameters kept in fp32.
 
+Every BatchNorm is a :class:`~..ops.fused_bn.FusedBatchNormAct2d`: BN, the
+residual add and the ReLU of a block run as one fused sm_100a op (2 reads + 1
+write forward) instead of three framework kernels; parameters, buffers and
+``state_dict`` keys are those of ``nn.BatchNorm2d``.
+
 The reference trains ``torchvision.models.resnet50()`` (``gossip_sgd.py:693-707``)
 initialised as in "ImageNet in 1 hour": zero gamma in the last BN of every
 residual block and N(0, 0.01) weights in the classifier -- see
@@ -18,6 +23,8 @@ from typing import List, Type
 
 import torch
 import torch.nn as nn
+
+from ..ops.fused_bn import FusedBatchNormAct2d as _BN
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -34,9 +41,9 @@ class BasicBlock(nn.Module):
     def __init__(self, cin, width, stride=1, downsample=None):
         super().__init__()
         self.conv1 = _conv3x3(cin, width, stride)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _BN(width)
         self.conv2 = _conv3x3(width, width)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _BN(width)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
@@ -46,9 +53,8 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return self.relu(out + identity)
+        out = self.bn1(self.conv1(x), relu=True)
+        return self.bn2(self.conv2(out), residual=identity, relu=True)
 
 
 class Bottleneck(nn.Module):
@@ -57,11 +63,11 @@ class Bottleneck(nn.Module):
     def __init__(self, cin, width, stride=1, downsample=None):
         super().__init__()
         self.conv1 = _conv1x1(cin, width)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _BN(width)
         self.conv2 = _conv3x3(width, width, stride)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _BN(width)
         self.conv3 = _conv1x1(width, width * self.expansion)
-        self.bn3 = nn.BatchNorm2d(width * self.expansion)
+        self.bn3 = _BN(width * self.expansion)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
@@ -71,10 +77,9 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return self.relu(out + identity)
+        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn2(self.conv2(out), relu=True)
+        return self.bn3(self.conv3(out), residual=identity, relu=True)
 
 
 class ResNet(nn.Module):
@@ -84,7 +89,7 @@ class ResNet(nn.Module):
         super().__init__()
         self.inplanes = base_width
         self.conv1 = nn.Conv2d(in_channels, base_width, 7, 2, 3, bias=False)
-        self.bn1 = nn.BatchNorm2d(base_width)
+        self.bn1 = _BN(base_width)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         self.layer1 = self._make_layer(block, base_width, layers[0])
@@ -104,14 +109,14 @@ class ResNet(nn.Module):
         downsample = None
         if stride != 1 or self.inplanes != width * block.expansion:
             downsample = nn.Sequential(_conv1x1(self.inplanes, width * block.expansion, stride),
-                                       nn.BatchNorm2d(width * block.expansion))
+                                       _BN(width * block.expansion))
         layers = [block(self.inplanes, width, stride, downsample)]
         self.inplanes = width * block.expansion
         layers += [block(self.inplanes, width) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.bn1(self.conv1(x), relu=True))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)
@@ -153,8 +158,8 @@ class TinyConvNet(nn.Module):
     def __init__(self, num_classes=10, width=16):
         super().__init__()
         self.features = nn.Sequential(
-            nn.Conv2d(3, width, 3, 2, 1, bias=False), nn.BatchNorm2d(width), nn.ReLU(inplace=True),
-            nn.Conv2d(width, 2 * width, 3, 2, 1, bias=False), nn.BatchNorm2d(2 * width),
+            nn.Conv2d(3, width, 3, 2, 1, bias=False), _BN(width), nn.ReLU(inplace=True),
+            nn.Conv2d(width, 2 * width, 3, 2, 1, bias=False), _BN(2 * width),
             nn.ReLU(inplace=True), nn.AdaptiveAvgPool2d((1, 1)))
         self.fc = nn.Linear(2 * width, num_classes)
 

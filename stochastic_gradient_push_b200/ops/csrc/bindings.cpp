@@ -299,8 +299,11 @@ static void zero_(torch::Tensor x)
     SGP_CUDA_CHECK(sgp_launch_zero(x.data_ptr(), bytes, at::cuda::getCurrentCUDAStream()));
 }
 
+void bind_bn(py::module& mod);   // bn_bindings.cpp
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
 {
+    bind_bn(mod);
     mod.doc() = "sm_100a gossip kernels + symmetric-memory runtime";
     mod.def("symm_alloc", &symm_alloc, "allocate IPC-exportable device memory -> (uint8 tensor, handle)");
     mod.def("symm_open", &symm_open, "map a peer's allocation -> uint8 tensor");

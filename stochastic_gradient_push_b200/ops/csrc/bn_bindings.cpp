@@ -1,0 +1,167 @@
+// torch bindings for the fused NHWC BatchNorm kernels (bn_kernels.cu)
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace py = pybind11;
+
+extern "C" {
+int bn_supported(long long M, int C);
+int bn_partial_rows(long long M, int C);
+cudaError_t bn_launch_stats(int dtype, const void* x, float* partial, long long M, int C, int G, cudaStream_t st);
+cudaError_t bn_launch_stats_finalize(const float* partial, int G, long long M, int C, const float* gamma,
+                                     const float* beta, float* rmean, float* rvar, long long* nbt,
+                                     float momentum, float eps, float* mean, float* invstd,
+                                     float* scale, float* shift, cudaStream_t st);
+cudaError_t bn_launch_eval_coeff(int C, const float* gamma, const float* beta, const float* rmean,
+                                 const float* rvar, float eps, float* scale, float* shift, cudaStream_t st);
+cudaError_t bn_launch_apply(int dtype, int relu, int add, const void* x, const void* res,
+                            const float* scale, const float* shift, void* y, long long M, int C, cudaStream_t st);
+cudaError_t bn_launch_bwd_reduce(int dtype, int mode, const void* dy, const void* x, const void* y,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, float* partial, void* dz, long long M, int C,
+                                 int G, cudaStream_t st);
+cudaError_t bn_launch_bwd_finalize(const float* partial, int G, long long M, int C, const float* scale,
+                                   const float* mean, const float* invstd, float* ggamma, float* gbeta,
+                                   float* c2, float* c3, cudaStream_t st);
+cudaError_t bn_launch_bwd_dx(int dtype, int mode, const void* dz, const void* x, const float* scale,
+                             const float* shift, const float* c2, const float* c3, void* dx,
+                             long long M, int C, cudaStream_t st);
+}
+
+#define BN_CHECK(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+static int dtype_code(const torch::Tensor& t)
+{
+    if (t.scalar_type() == torch::kBFloat16) return 0;
+    if (t.scalar_type() == torch::kFloat32) return 1;
+    throw std::runtime_error("fused BN supports bf16 / fp32 activations");
+}
+
+// x must be NHWC-dense: a 4-D channels_last tensor or a 2-D [M, C] matrix
+static void nhwc_dims(const torch::Tensor& x, long long& M, int& C)
+{
+    if (x.dim() == 4) {
+        TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "fused BN needs channels_last input");
+        C = (int)x.size(1);
+        M = x.numel() / C;
+    } else {
+        TORCH_CHECK(x.dim() == 2 && x.is_contiguous());
+        C = (int)x.size(1);
+        M = x.size(0);
+    }
+}
+
+static bool bn_can_fuse(const torch::Tensor& x)
+{
+    if (!x.is_cuda()) return false;
+    if (x.scalar_type() != torch::kBFloat16 && x.scalar_type() != torch::kFloat32) return false;
+    if (x.dim() == 4) { if (!x.is_contiguous(at::MemoryFormat::ChannelsLast)) return false; }
+    else if (!(x.dim() == 2 && x.is_contiguous())) return false;
+    const int C = (int)x.size(1);
+    return bn_supported(x.numel() / C, C) != 0;
+}
+
+// returns (y, mean, invstd, scale, shift)
+static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torch::Tensor> residual,
+                                             torch::Tensor gamma, torch::Tensor beta,
+                                             c10::optional<torch::Tensor> running_mean,
+                                             c10::optional<torch::Tensor> running_var,
+                                             c10::optional<torch::Tensor> num_batches_tracked,
+                                             bool training, double momentum, double eps, bool relu)
+{
+    long long M; int C;
+    nhwc_dims(x, M, C);
+    TORCH_CHECK(bn_supported(M, C), "unsupported channel count ", C);
+    TORCH_CHECK(gamma.scalar_type() == torch::kFloat32 && beta.scalar_type() == torch::kFloat32);
+    const int dt = dtype_code(x);
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto st = at::cuda::getCurrentCUDAStream();
+    auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
+    auto y = torch::empty_like(x);
+    auto coef = torch::empty({4, C}, fopt);      // mean, invstd, scale, shift
+    float* mean = coef.data_ptr<float>();
+    float* invstd = mean + C; float* scale = mean + 2 * C; float* shift = mean + 3 * C;
+    const bool has_res = residual.has_value() && residual->defined();
+    if (has_res) TORCH_CHECK(residual->sizes() == x.sizes() && residual->scalar_type() == x.scalar_type()
+                             && residual->strides() == x.strides());
+    if (training) {
+        const int G = bn_partial_rows(M, C);
+        auto partial = torch::empty({G, 2, C}, fopt);
+        BN_CHECK(bn_launch_stats(dt, x.data_ptr(), partial.data_ptr<float>(), M, C, G, st));
+        float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
+        if (running_mean.has_value() && running_mean->defined()) {
+            rm = running_mean->data_ptr<float>();
+            rv = running_var->data_ptr<float>();
+        }
+        if (num_batches_tracked.has_value() && num_batches_tracked->defined())
+            nbt = reinterpret_cast<long long*>(num_batches_tracked->data_ptr<int64_t>());
+        BN_CHECK(bn_launch_stats_finalize(partial.data_ptr<float>(), G, M, C, gamma.data_ptr<float>(),
+                                          beta.data_ptr<float>(), rm, rv, nbt, (float)momentum,
+                                          (float)eps, mean, invstd, scale, shift, st));
+    } else {
+        TORCH_CHECK(running_mean.has_value() && running_var.has_value());
+        BN_CHECK(bn_launch_eval_coeff(C, gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                                      running_mean->data_ptr<float>(), running_var->data_ptr<float>(),
+                                      (float)eps, scale, shift, st));
+    }
+    BN_CHECK(bn_launch_apply(dt, relu ? 1 : 0, has_res ? 1 : 0, x.data_ptr(),
+                             has_res ? residual->data_ptr() : nullptr, scale, shift, y.data_ptr(),
+                             M, C, st));
+    return {y, coef};
+}
+
+// returns (dx, dres or undefined, grad_gamma, grad_beta)
+static std::vector<torch::Tensor> bn_backward(torch::Tensor dy, torch::Tensor x,
+                                              c10::optional<torch::Tensor> y, torch::Tensor coef,
+                                              bool relu, bool add)
+{
+    long long M; int C;
+    nhwc_dims(x, M, C);
+    const int dt = dtype_code(x);
+    TORCH_CHECK(dy.scalar_type() == x.scalar_type());
+    if (dy.strides() != x.strides()) dy = dy.contiguous(x.dim() == 4 ? at::MemoryFormat::ChannelsLast
+                                                                     : at::MemoryFormat::Contiguous);
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto st = at::cuda::getCurrentCUDAStream();
+    auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
+    const float* mean = coef.data_ptr<float>();
+    const float* invstd = mean + C; const float* scale = mean + 2 * C; const float* shift = mean + 3 * C;
+    const int mode = add ? 2 : (relu ? 1 : 0);
+    TORCH_CHECK(!add || relu, "residual add without ReLU is plain autograd (not fused)");
+    if (mode == 2) TORCH_CHECK(y.has_value() && y->defined() && y->strides() == x.strides());
+    const int G = bn_partial_rows(M, C);
+    auto partial = torch::empty({G, 2, C}, fopt);
+    auto grads = torch::empty({4, C}, fopt);    // grad_gamma, grad_beta, c2, c3
+    float* gg = grads.data_ptr<float>();
+    torch::Tensor dz;
+    if (mode == 2) dz = torch::empty_like(x);
+    BN_CHECK(bn_launch_bwd_reduce(dt, mode, dy.data_ptr(), x.data_ptr(),
+                                  mode == 2 ? y->data_ptr() : nullptr, scale, shift, mean, invstd,
+                                  partial.data_ptr<float>(), mode == 2 ? dz.data_ptr() : nullptr,
+                                  M, C, G, st));
+    BN_CHECK(bn_launch_bwd_finalize(partial.data_ptr<float>(), G, M, C, scale, mean, invstd,
+                                    gg, gg + C, gg + 2 * C, gg + 3 * C, st));
+    auto dx = torch::empty_like(x);
+    BN_CHECK(bn_launch_bwd_dx(dt, mode == 1 ? 1 : 0, mode == 2 ? dz.data_ptr() : dy.data_ptr(),
+                              x.data_ptr(), scale, shift, gg + 2 * C, gg + 3 * C, dx.data_ptr(),
+                              M, C, st));
+    return {dx, dz, grads.select(0, 0), grads.select(0, 1)};
+}
+
+void bind_bn(py::module& mod)
+{
+    mod.def("bn_can_fuse", &bn_can_fuse);
+    mod.def("bn_forward", &bn_forward);
+    mod.def("bn_backward", &bn_backward);
+}

@@ -1,0 +1,108 @@
+"""
+FusedBatchNormAct2d: BatchNorm2d (+ residual add) (+ ReLU) as ONE op, backed by
+the sm_100a NHWC kernels in ``csrc/bn_kernels.cu``.
+
+Why it exists: an ncu launch list of the ResNet-50 training step at batch 256
+(``profiles/launches_r1_bs256_before_fused_bn.csv``) attributes ~59 % of the
+GPU time to the framework's channels-last BatchNorm kernels and ~13 % to
+stand-alone ReLU / add / cast kernels, versus ~15 % for the tensor-core
+convolutions.  All of that work is memory-bound, so it is rewritten as the
+minimum number of 16-byte-vectorised passes over HBM (forward 2 reads + 1
+write instead of 5 reads + 3 writes; backward recomputes the ReLU mask from the
+saved input instead of reading a mask/output tensor).
+
+The module is a drop-in ``nn.BatchNorm2d`` subclass (same parameters, buffers
+and ``state_dict`` keys); ``forward(x, residual=None, relu=False)``.  Anything
+the kernels do not cover (CPU tensors, NCHW layout, C % 8 != 0, fp16/fp64)
+runs the reference composition ``relu(batch_norm(x) + residual)``, which is
+also the oracle in the numerics tests.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import native
+
+
+def _can_fuse(x: torch.Tensor) -> bool:
+    if not x.is_cuda or not native.available():
+        return False
+    return bool(native.load().bn_can_fuse(x))
+
+
+class _FusedBNAct(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt,
+                training, momentum, eps, relu):
+        C = native.load()
+        y, coef = C.bn_forward(x, residual, weight, bias, running_mean, running_var, nbt,
+                               training, momentum, eps, relu)
+        ctx.relu = relu
+        ctx.add = residual is not None
+        ctx.training = training
+        if ctx.add:
+            ctx.save_for_backward(x, y, coef, weight)
+        else:
+            ctx.save_for_backward(x, coef, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C = native.load()
+        if ctx.add:
+            x, y, coef, weight = ctx.saved_tensors
+        else:
+            x, coef, weight = ctx.saved_tensors
+            y = None
+        if not ctx.training:
+            # eval-mode BN is an affine map: dx = scale * dz
+            scale = coef[2].to(dy.dtype).view(1, -1, 1, 1)
+            dz = dy
+            if ctx.relu:
+                out = y if ctx.add else torch.relu(F.batch_norm(x, None, None, training=False))
+                dz = dy * (out > 0)
+            return dz * scale, (dz if ctx.add else None), None, None, None, None, None, \
+                None, None, None, None
+        dx, dz, ggamma, gbeta = C.bn_backward(dy, x, y, coef, ctx.relu, ctx.add)
+        return dx, (dz if ctx.add else None), ggamma, gbeta, None, None, None, None, None, None, None
+
+
+def fused_bn_act(x, weight, bias, running_mean, running_var, num_batches_tracked=None,
+                 residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+    """Functional form; falls back to plain PyTorch when the kernels cannot run."""
+    fusable = _can_fuse(x) and weight is not None and weight.dtype == torch.float32 \
+        and (residual is None or (relu and residual.dtype == x.dtype
+                                  and residual.stride() == x.stride()))
+    if fusable and (training or not torch.is_grad_enabled() or not x.requires_grad):
+        return _FusedBNAct.apply(x, residual, weight, bias, running_mean, running_var,
+                                 num_batches_tracked, training, momentum, eps, relu)
+    return reference_bn_act(x, weight, bias, running_mean, running_var, num_batches_tracked,
+                            residual, relu, training, momentum, eps)
+
+
+def reference_bn_act(x, weight, bias, running_mean, running_var, num_batches_tracked=None,
+                     residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+    if training and num_batches_tracked is not None:
+        num_batches_tracked.add_(1)
+    y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+class FusedBatchNormAct2d(nn.BatchNorm2d):
+    """``y = relu?(bn(x) (+ residual)?)`` -- see module docstring."""
+
+    def forward(self, x, residual=None, relu=False):
+        training = self.training or (self.running_mean is None)
+        momentum = 0.1 if self.momentum is None else self.momentum
+        return fused_bn_act(
+            x, self.weight, self.bias,
+            self.running_mean if self.track_running_stats else None,
+            self.running_var if self.track_running_stats else None,
+            self.num_batches_tracked if (self.track_running_stats and training) else None,
+            residual=residual, relu=relu, training=training, momentum=momentum, eps=self.eps)

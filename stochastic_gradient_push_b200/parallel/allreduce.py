@@ -157,6 +157,8 @@ class ARTrainer(GossipTrainer):
         self.graph = None
         self.static_in = self.static_tgt = self.static_loss = self.static_out = None
         self._eager_steps = 0
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._stage = self._stage_tgt = None
         self._stage_ready = torch.cuda.Event()

@@ -56,6 +56,10 @@ class GossipTrainer(object):
         self.static_loss = None
         self.static_out = None
         self._eager_steps = 0
+        # every launch of the step runs on ONE dedicated side stream: autograd's
+        # AccumulateGrad nodes are then created on the stream the graph is captured on
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._stage = None
         self._stage_tgt = None
@@ -78,7 +82,7 @@ class GossipTrainer(object):
             loss = self.criterion(out.float(), self.static_tgt)
         loss.backward()
         self.static_loss.copy_(loss.detach())
-        self.static_out = out
+        self.static_out = out.detach()
 
     def _gossip_kernels(self, first: bool):
         """The gossip / optimizer launches of one step.  ``first``: no gradient
@@ -133,7 +137,8 @@ class GossipTrainer(object):
         self._stage_tgt = torch.empty_like(self.static_tgt)
         self.static_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self._loss_ring = torch.zeros(1024, dtype=torch.float32).pin_memory()
-        self._stage_free.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._stage_free.record(self.stream)
 
     def _set_lr(self):
         g = self.opt.param_groups[0]
@@ -152,13 +157,14 @@ class GossipTrainer(object):
         self._prefetched = True
 
     def _load_inputs(self, batch, target):
-        main = torch.cuda.current_stream(self.device)
+        main = self.stream
         if batch is not None and not self._prefetched:
             self.prefetch(batch, target)
         main.wait_event(self._stage_ready)
-        self.static_in.copy_(self._stage, non_blocking=True)
-        self.static_tgt.copy_(self._stage_tgt, non_blocking=True)
-        self._stage_free.record(main)
+        with torch.cuda.stream(main):
+            self.static_in.copy_(self._stage, non_blocking=True)
+            self.static_tgt.copy_(self._stage_tgt, non_blocking=True)
+            self._stage_free.record(main)
         self._prefetched = False
 
     def step(self, batch=None, target=None, next_batch=None, next_target=None,
@@ -180,7 +186,8 @@ class GossipTrainer(object):
         self._run()
         slot = self._loss_slot
         if read_loss:
-            self._loss_ring[slot:slot + 1].copy_(self.static_loss.view(1), non_blocking=True)
+            with torch.cuda.stream(self.stream):
+                self._loss_ring[slot:slot + 1].copy_(self.static_loss.view(1), non_blocking=True)
             self._loss_slot = (slot + 1) % self._loss_ring.numel()
         return slot
 
@@ -191,8 +198,11 @@ class GossipTrainer(object):
         self._run()
 
     def _run(self):
+        with torch.cuda.stream(self.stream):
+            self._run_on_stream()
+
+    def _run_on_stream(self):
         self._set_lr()
-        e = self.engine
         if self.graph is not None:
             self.graph.replay()
             self._after_replay()
@@ -216,7 +226,7 @@ class GossipTrainer(object):
         torch.cuda.synchronize(self.device)
         steps_before = self.engine.steps
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode='thread_local'):
             self._one_step(first=False)
         # capture does not execute: undo the host-side step mirror advance
         self.engine.steps = steps_before
@@ -225,6 +235,7 @@ class GossipTrainer(object):
     def finish(self):
         """Drain: apply the last deferred SGD / residual (overlap) and sync."""
         if self.overlap and self.gossip:
-            self.engine.local(sgd=True, fold=True)
+            with torch.cuda.stream(self.stream):
+                self.engine.local(sgd=True, fold=True)
         torch.cuda.synchronize(self.device)
         self.engine.check()

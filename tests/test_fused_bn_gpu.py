@@ -1,0 +1,93 @@
+"""Fused NHWC BatchNorm(+add)(+ReLU) kernels vs the plain PyTorch fp32 composition."""
+import pytest
+import torch
+
+from stochastic_gradient_push_b200.ops.fused_bn import (FusedBatchNormAct2d, fused_bn_act,
+                                                        reference_bn_act, _can_fuse)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fn, x, res, w, b, relu, dtype):
+    x = x.detach().clone().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = None
+    if res is not None:
+        r = res.detach().clone().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = w.detach().clone().requires_grad_(True)
+    b = b.detach().clone().requires_grad_(True)
+    C = w.numel()
+    rm, rv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
+    nbt = torch.zeros((), dtype=torch.long, device='cuda')
+    y = fn(x, w, b, rm, rv, nbt, residual=r, relu=relu, training=True, momentum=0.1, eps=1e-5)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    dy = torch.randn(y.shape, device='cuda', generator=g).to(dtype).contiguous(
+        memory_format=torch.channels_last)
+    y.backward(dy)
+    return dict(y=y.detach().float(), dx=x.grad.float(), dres=None if r is None else r.grad.float(),
+                dw=w.grad, db=b.grad, rm=rm, rv=rv, nbt=int(nbt))
+
+
+@pytest.mark.parametrize('shape', [(8, 64, 14, 14), (4, 256, 7, 9), (3, 2048, 4, 4), (5, 24, 6, 5),
+                                   (16, 512, 2, 2)])
+@pytest.mark.parametrize('relu,add', [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_fused_bn_matches_reference(shape, relu, add, dtype):
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    x = torch.randn(shape, device='cuda') * 2 + 0.5
+    res = torch.randn(shape, device='cuda') if add else None
+    w = torch.rand(C, device='cuda') + 0.5
+    b = torch.randn(C, device='cuda') * 0.1
+    assert _can_fuse(x.to(dtype).contiguous(memory_format=torch.channels_last))
+    got = _run(fused_bn_act, x, res, w, b, relu, dtype)
+    # oracle: same (possibly bf16-rounded) inputs, fp32 math
+    xq = x.to(dtype).float()
+    rq = None if res is None else res.to(dtype).float()
+    want = _run(reference_bn_act, xq, rq, w, b, relu, torch.float32)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(got['y'], want['y'], **tol)
+    torch.testing.assert_close(got['dx'], want['dx'], **tol)
+    if add:
+        torch.testing.assert_close(got['dres'], want['dres'], **tol)
+    stat_tol = dict(rtol=1e-3, atol=1e-3) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    M = N * H * W
+    torch.testing.assert_close(got['dw'], want['dw'], rtol=stat_tol['rtol'], atol=stat_tol['atol'] * M ** 0.5)
+    torch.testing.assert_close(got['db'], want['db'], rtol=stat_tol['rtol'], atol=stat_tol['atol'] * M ** 0.5)
+    torch.testing.assert_close(got['rm'], want['rm'], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got['rv'], want['rv'], rtol=1e-3, atol=1e-3)
+    assert got['nbt'] == 1
+
+
+def test_module_eval_and_fallbacks():
+    bn = FusedBatchNormAct2d(32).cuda()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    ref = torch.nn.BatchNorm2d(32).cuda()
+    ref.load_state_dict(bn.state_dict())
+    x = torch.randn(4, 32, 5, 5, device='cuda').contiguous(memory_format=torch.channels_last)
+    bn.eval(), ref.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(bn(x, relu=True), torch.relu(ref(x)), rtol=1e-5, atol=1e-5)
+    # NCHW input -> reference path, identical semantics
+    bn.train(), ref.train()
+    xn = torch.randn(4, 32, 5, 5, device='cuda')
+    torch.testing.assert_close(bn(xn), ref(xn), rtol=1e-5, atol=1e-5)
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+
+
+def test_resnet50_fused_matches_torchvision_fwd_bwd():
+    import torchvision
+    from stochastic_gradient_push_b200.models import resnet50
+    torch.manual_seed(0)
+    tv = torchvision.models.resnet50().cuda().to(memory_format=torch.channels_last)
+    ours = resnet50().cuda().to(memory_format=torch.channels_last)
+    ours.load_state_dict(tv.state_dict())
+    x = torch.randn(8, 3, 64, 64, device='cuda').contiguous(memory_format=torch.channels_last)
+    yo, yt = ours(x), tv(x)
+    torch.testing.assert_close(yo, yt, rtol=1e-3, atol=1e-3)
+    yo.square().mean().backward()
+    yt.square().mean().backward()
+    for (n, p), q in zip(ours.named_parameters(), tv.parameters()):
+        torch.testing.assert_close(p.grad, q.grad, rtol=2e-2, atol=2e-3, msg=lambda m: n + ': ' + m)
+    for (n, b), c in zip(ours.named_buffers(), tv.buffers()):
+        torch.testing.assert_close(b.float(), c.float(), rtol=1e-3, atol=1e-3)
