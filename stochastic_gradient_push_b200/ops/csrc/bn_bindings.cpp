@@ -97,7 +97,7 @@ static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torc
                              && residual->strides() == x.strides());
     if (training) {
         const int G = bn_partial_rows(M, C);
-        auto partial = torch::empty({G, 2, C}, fopt);
+        auto partial = torch::empty({G + 1, 2, C}, fopt);   // last row carries the shift K
         BN_CHECK(bn_launch_stats(dt, x.data_ptr(), partial.data_ptr<float>(), M, C, G, st));
         float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
         if (running_mean.has_value() && running_mean->defined()) {

@@ -147,6 +147,14 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
         const long long stride = (long long)gridDim.x * mp.rpi;
         long long r = (long long)blockIdx.x * mp.rpi + mp.rl;
         const T* base = x + mp.cv * BN_VEC;
+        // shifted sums: accumulate (x - K) with K = x[row 0] so that
+        // var = E[(x-K)^2] - E[x-K]^2 does not cancel when |mean| >> std
+        const F8 k = Io<T>::load(base);
+        if (blockIdx.x == 0 && mp.rl == 0) {
+            float* krow = partial + (size_t)gridDim.x * 2 * C + mp.cv * BN_VEC;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) krow[i] = k.v[i];
+        }
         for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
             typename Io<T>::raw_t raw[BN_UNROLL];
 #pragma unroll
@@ -155,36 +163,83 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
             for (int u = 0; u < BN_UNROLL; ++u) {
                 const F8 d = Io<T>::decode(raw[u]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { s.v[i] += d.v[i]; q.v[i] = fmaf(d.v[i], d.v[i], q.v[i]); }
+                for (int i = 0; i < 8; ++i) {
+                    const float c = d.v[i] - k.v[i];
+                    s.v[i] += c; q.v[i] = fmaf(c, c, q.v[i]);
+                }
             }
         }
         for (; r < M; r += stride) {
             const F8 d = Io<T>::load(base + r * C);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s.v[i] += d.v[i]; q.v[i] = fmaf(d.v[i], d.v[i], q.v[i]); }
+            for (int i = 0; i < 8; ++i) {
+                const float c = d.v[i] - k.v[i];
+                s.v[i] += c; q.v[i] = fmaf(c, c, q.v[i]);
+            }
         }
     }
     reduce_store_partials(mp, s, q, partial, C);
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int G, long long M, int C,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         float* running_mean, float* running_var, long long* nbt,
-                                         float momentum, float eps,
-                                         float* __restrict__ mean, float* __restrict__ invstd,
-                                         float* __restrict__ scale, float* __restrict__ shift)
+// Finalize kernels: a CTA owns 32 channels; its 1024 threads are 32 partial-row
+// lanes x 32 channels, so the G (<= 592) partial rows are summed with ~G/128
+// dependent steps per thread instead of G (a one-thread-per-channel loop over G
+// L2-latency-bound loads took ~78 us per launch -- longer than the streaming
+// kernels it finalises).
+#define BN_FIN_THREADS 1024
+
+__device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int G, int C,
+                                             float& s_out, float& q_out, bool& owner, int& ch)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt != nullptr) *nbt += 1;
-    if (c >= C) return;
-    float s = 0.f, q = 0.f;
-    for (int g = 0; g < G; ++g) {
-        s += partial[(size_t)g * 2 * C + c];
-        q += partial[(size_t)g * 2 * C + C + c];
+    __shared__ float sm_s[32][33];
+    __shared__ float sm_q[32][33];
+    const int cl = threadIdx.x & 31;
+    const int lane = threadIdx.x >> 5;
+    ch = blockIdx.x * 32 + cl;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    if (ch < C) {
+        int g = lane;
+        for (; g + 32 < G; g += 64) {
+            s0 += partial[(size_t)g * 2 * C + ch];
+            q0 += partial[(size_t)g * 2 * C + C + ch];
+            s1 += partial[(size_t)(g + 32) * 2 * C + ch];
+            q1 += partial[(size_t)(g + 32) * 2 * C + C + ch];
+        }
+        if (g < G) {
+            s0 += partial[(size_t)g * 2 * C + ch];
+            q0 += partial[(size_t)g * 2 * C + C + ch];
+        }
     }
+    sm_s[lane][cl] = s0 + s1;
+    sm_q[lane][cl] = q0 + q1;
+    __syncthreads();
+    owner = (lane == 0) && (ch < C);
+    float s = 0.f, q = 0.f;
+    if (owner) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) { s += sm_s[l][cl]; q += sm_q[l][cl]; }
+    }
+    s_out = s;
+    q_out = q;
+}
+
+__global__ void __launch_bounds__(BN_FIN_THREADS)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int G, long long M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* running_mean, float* running_var, long long* nbt,
+                         float momentum, float eps,
+                         float* __restrict__ mean, float* __restrict__ invstd,
+                         float* __restrict__ scale, float* __restrict__ shift)
+{
+    float s, q; bool owner; int c;
+    sum_partials(partial, G, C, s, q, owner, c);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+    if (!owner) return;
+    const float k = partial[(size_t)G * 2 * C + c];          // the shift K = x[row 0]
     const float inv_m = 1.f / (float)M;
-    const float mu = s * inv_m;
-    const float var = fmaxf(fmaf(-mu, mu, q * inv_m), 0.f);
+    const float ds = s * inv_m;
+    const float mu = k + ds;
+    const float var = fmaxf(fmaf(-ds, ds, q * inv_m), 0.f);
     const float is = rsqrtf(var + eps);
     mean[c] = mu;
     invstd[c] = is;
@@ -318,19 +373,16 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 
 // per-channel: grad_gamma, grad_beta and the dx coefficients
 //   dx = scale*(dz - sdz/M - xhat*sdzx/M) = c1*dz - c2*x + c3
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, long long M, int C,
-                                       const float* __restrict__ scale, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd,
-                                       float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
-                                       float* __restrict__ c2, float* __restrict__ c3)
+__global__ void __launch_bounds__(BN_FIN_THREADS)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, long long M, int C,
+                       const float* __restrict__ scale, const float* __restrict__ mean,
+                       const float* __restrict__ invstd,
+                       float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
+                       float* __restrict__ c2, float* __restrict__ c3)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float s = 0.f, q = 0.f;
-    for (int g = 0; g < G; ++g) {
-        s += partial[(size_t)g * 2 * C + c];
-        q += partial[(size_t)g * 2 * C + C + c];
-    }
+    float s, q; bool owner; int c;
+    sum_partials(partial, G, C, s, q, owner, c);
+    if (!owner) return;
     grad_beta[c] = s;
     grad_gamma[c] = q;
     const float inv_m = 1.f / (float)M;
@@ -421,7 +473,7 @@ cudaError_t bn_launch_stats_finalize(const float* partial, int G, long long M, i
                                      float momentum, float eps, float* mean, float* invstd,
                                      float* scale, float* shift, cudaStream_t st)
 {
-    bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, G, M, C, gamma, beta, rmean, rvar,
+    bn_stats_finalize_kernel<<<(C + 31) / 32, BN_FIN_THREADS, 0, st>>>(partial, G, M, C, gamma, beta, rmean, rvar,
                                                               nbt, momentum, eps, mean, invstd, scale, shift);
     return cudaGetLastError();
 }
@@ -475,7 +527,7 @@ cudaError_t bn_launch_bwd_finalize(const float* partial, int G, long long M, int
                                    const float* mean, const float* invstd, float* ggamma, float* gbeta,
                                    float* c2, float* c3, cudaStream_t st)
 {
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, G, M, C, scale, mean, invstd,
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, BN_FIN_THREADS, 0, st>>>(partial, G, M, C, scale, mean, invstd,
                                                             ggamma, gbeta, c2, c3);
     return cudaGetLastError();
 }

@@ -28,7 +28,7 @@ def _run(fn, x, res, w, b, relu, dtype):
 
 
 @pytest.mark.parametrize('shape', [(8, 64, 14, 14), (4, 256, 7, 9), (3, 2048, 4, 4), (5, 24, 6, 5),
-                                   (16, 512, 2, 2)])
+                                   (16, 512, 2, 2), (32, 64, 56, 56), (8, 2048, 2, 2)])
 @pytest.mark.parametrize('relu,add', [(False, False), (True, False), (True, True)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_fused_bn_matches_reference(shape, relu, add, dtype):
@@ -56,6 +56,17 @@ def test_fused_bn_matches_reference(shape, relu, add, dtype):
     torch.testing.assert_close(got['rm'], want['rm'], rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(got['rv'], want['rv'], rtol=1e-3, atol=1e-3)
     assert got['nbt'] == 1
+
+
+def test_variance_is_stable_when_mean_dominates():
+    """|mean| >> std: a naive E[x^2]-E[x]^2 in fp32 loses the variance."""
+    torch.manual_seed(0)
+    x = (1000.0 + 0.05 * torch.randn(16, 64, 8, 8, device='cuda')).contiguous(
+        memory_format=torch.channels_last)
+    w, b = torch.ones(64, device='cuda'), torch.zeros(64, device='cuda')
+    y = fused_bn_act(x, w, b, None, None, None, training=True)
+    ref = torch.nn.functional.batch_norm(x.double(), None, None, w.double(), b.double(), True)
+    torch.testing.assert_close(y.double(), ref, rtol=5e-3, atol=5e-3)
 
 
 def test_module_eval_and_fallbacks():
