@@ -24,7 +24,7 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
-from ..ops.fused_bn import FusedBatchNormAct2d as _BN
+from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -91,7 +91,7 @@ class ResNet(nn.Module):
         self.conv1 = nn.Conv2d(in_channels, base_width, 7, 2, 3, bias=False)
         self.bn1 = _BN(base_width)
         self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.maxpool = MaxPool2dNHWC(3, 2, 1)
         self.layer1 = self._make_layer(block, base_width, layers[0])
         self.layer2 = self._make_layer(block, base_width * 2, layers[1], 2)
         self.layer3 = self._make_layer(block, base_width * 4, layers[2], 2)

@@ -159,8 +159,53 @@ static std::vector<torch::Tensor> bn_backward(torch::Tensor dy, torch::Tensor x,
     return {dx, dz, grads.select(0, 0), grads.select(0, 1)};
 }
 
+// ---------------------------------------------------------------------------
+// NHWC max-pool
+// ---------------------------------------------------------------------------
+extern "C" {
+cudaError_t pool_launch_fwd(int dtype, const void* x, void* y, uint8_t* code, int N, int H, int W, int C,
+                            int OH, int OW, int k, int s, int p, cudaStream_t st);
+cudaError_t pool_launch_bwd(int dtype, const void* dy, const uint8_t* code, void* dx, int N, int H, int W,
+                            int C, int OH, int OW, int k, int s, int p, cudaStream_t st);
+}
+
+static bool pool_can_fuse(const torch::Tensor& x, int k, int s, int p)
+{
+    return x.is_cuda() && x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast)
+        && (x.scalar_type() == torch::kBFloat16 || x.scalar_type() == torch::kFloat32)
+        && x.size(1) % 8 == 0 && k >= 1 && k <= 11 && s >= 1 && p >= 0 && 2 * p <= k;
+}
+
+// returns (y, code)
+static std::vector<torch::Tensor> maxpool_forward(torch::Tensor x, int k, int s, int p)
+{
+    TORCH_CHECK(pool_can_fuse(x, k, s, p));
+    const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+    const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto y = torch::empty({N, C, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    auto code = torch::empty({N, OH, OW, C}, x.options().dtype(torch::kUInt8));
+    BN_CHECK(pool_launch_fwd(dtype_code(x), x.data_ptr(), y.data_ptr(), code.data_ptr<uint8_t>(),
+                             N, H, W, C, OH, OW, k, s, p, at::cuda::getCurrentCUDAStream()));
+    return {y, code};
+}
+
+static torch::Tensor maxpool_backward(torch::Tensor dy, torch::Tensor code, int H, int W, int k, int s, int p)
+{
+    const int N = (int)dy.size(0), C = (int)dy.size(1), OH = (int)dy.size(2), OW = (int)dy.size(3);
+    if (!dy.is_contiguous(at::MemoryFormat::ChannelsLast)) dy = dy.contiguous(at::MemoryFormat::ChannelsLast);
+    c10::cuda::CUDAGuard guard(dy.get_device());
+    auto dx = torch::empty({N, C, H, W}, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
+    BN_CHECK(pool_launch_bwd(dtype_code(dy), dy.data_ptr(), code.data_ptr<uint8_t>(), dx.data_ptr(),
+                             N, H, W, C, OH, OW, k, s, p, at::cuda::getCurrentCUDAStream()));
+    return dx;
+}
+
 void bind_bn(py::module& mod)
 {
+    mod.def("pool_can_fuse", &pool_can_fuse);
+    mod.def("maxpool_forward", &maxpool_forward);
+    mod.def("maxpool_backward", &maxpool_backward);
     mod.def("bn_can_fuse", &bn_can_fuse);
     mod.def("bn_forward", &bn_forward);
     mod.def("bn_backward", &bn_backward);

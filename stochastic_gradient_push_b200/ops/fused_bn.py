@@ -106,3 +106,38 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
             self.running_var if self.track_running_stats else None,
             self.num_batches_tracked if (self.track_running_stats and training) else None,
             residual=residual, relu=relu, training=training, momentum=momentum, eps=self.eps)
+
+
+# --------------------------------------------------------------------------- #
+# NHWC max-pool
+# --------------------------------------------------------------------------- #
+class _MaxPoolNHWC(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        C = native.load()
+        y, code = C.maxpool_forward(x, k, s, p)
+        ctx.save_for_backward(code)
+        ctx.geom = (x.shape[2], x.shape[3], k, s, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C = native.load()
+        (code,) = ctx.saved_tensors
+        H, W, k, s, p = ctx.geom
+        return C.maxpool_backward(dy, code, H, W, k, s, p), None, None, None
+
+
+class MaxPool2dNHWC(nn.MaxPool2d):
+    """``nn.MaxPool2d`` whose channels-last CUDA path is the sm_100a gather
+    kernel pair in ``csrc/pool_kernels.cu`` (1-byte argmax codes instead of
+    int64 indices, atomic-free backward).  Other inputs use the stock op."""
+
+    def forward(self, x):
+        k, s, p = self.kernel_size, self.stride, self.padding
+        simple = all(isinstance(v, int) for v in (k, s, p)) and self.dilation == 1 \
+            and not self.ceil_mode and not self.return_indices
+        if simple and x.is_cuda and native.available() and native.load().pool_can_fuse(x, k, s, p):
+            return _MaxPoolNHWC.apply(x, k, s, p)
+        return super().forward(x)
