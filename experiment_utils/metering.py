@@ -1,0 +1,2 @@
+"""Alias (``experiment_utils/metering.py``)."""
+from stochastic_gradient_push_b200.utils.metering import Meter  # noqa: F401

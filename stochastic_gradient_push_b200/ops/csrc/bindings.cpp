@@ -339,6 +339,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
     mod.attr("F_NO_ROTATE") = (unsigned)SGP_F_NO_ROTATE;
     mod.attr("F_PUBLISH") = (unsigned)SGP_F_PUBLISH;
     mod.attr("F_IN_NUMER") = (unsigned)SGP_F_IN_NUMER;
+    mod.attr("F_KEEP_Z") = (unsigned)SGP_F_KEEP_Z;
+    mod.attr("F_SELF_FROM_Z") = (unsigned)SGP_F_SELF_FROM_Z;
 
     py::class_<GossipContext>(mod, "GossipContext")
         .def(py::init<torch::Tensor, c10::optional<torch::Tensor>, c10::optional<torch::Tensor>,

@@ -85,6 +85,8 @@ struct SgpHyper {
 #define SGP_F_NO_ROTATE  (1u << 7)   // do not advance step (flush kernels)
 #define SGP_F_PUBLISH    (1u << 8)   // write outbox + release flags
 #define SGP_F_IN_NUMER   (1u << 9)   // z already holds the numerator x (external optimizer)
+#define SGP_F_KEEP_Z     (1u << 10)  // phase 1 publishes a snapshot but leaves z untouched
+#define SGP_F_SELF_FROM_Z (1u << 11) // phase 2 mixes the CURRENT z (not the published snapshot)
 
 struct SgpArgs {
     // local buffers (length n, n % SGP_CHUNK == 0)

@@ -125,7 +125,7 @@ sgp_step_kernel(const SgpArgs a)
         }
 
         const float inv_w1 = 1.f / w1;
-        const bool write_z = !(flags & SGP_F_PHASE2);
+        const bool write_z = !(flags & SGP_F_PHASE2) && !(flags & SGP_F_KEEP_Z);
 
         for (long long c = b; c < nchunks; c += gridDim.x) {
             const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
@@ -191,7 +191,9 @@ sgp_step_kernel(const SgpArgs a)
         }
     }
 
-    float w_next = (flags & SGP_F_PUBLISH) ? row.self_w * w1 : w1;
+    // overlap publish keeps the self-loop share locally (w <- self_w * w1); a
+    // snapshot-only publish (AD-PSGD) leaves the weight alone
+    float w_next = ((flags & SGP_F_PUBLISH) && !(flags & SGP_F_KEEP_Z)) ? row.self_w * w1 : w1;
 
     // ---------------- phase 2: pull + mix ----------------------------------
     if (flags & SGP_F_PHASE2) {
@@ -230,8 +232,11 @@ sgp_step_kernel(const SgpArgs a)
 #pragma unroll
                 for (int u = 0; u < SGP_UNROLL; ++u) {
                     const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                    acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first),
-                                  row.self_w);
+                    // own term: the snapshot this CTA published, or (AD-PSGD) the live
+                    // parameters, which may already carry newer local SGD updates
+                    const float* own = (flags & SGP_F_SELF_FROM_Z) ? a.z : my_out;
+                    acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(own + i), pol_first),
+                                  (flags & SGP_F_SELF_FROM_Z) ? row.self_w * w0 : row.self_w);
                 }
                 // peer loads: all UNROLL requests of one peer in flight together
                 for (int k = 0; k < row.n_in; ++k) {

