@@ -351,8 +351,18 @@ class BilatGossipDataParallel(Module):
                 time.sleep(self._poll)
 
     def _loop_c10d(self):
+        """Same protocol over isend/irecv.  Neither role ever blocks the loop:
+        a rank whose partner has gone quiet (finished, validating, slow) keeps
+        applying its own gradients -- the reference's active rank blocks inside
+        ``mix`` here (``gossip/gossiper.py:290-299``)."""
         cfg = dict(self.dist_config)
         alone = self.gossiper is None
+        g = self.gossiper
+        tr = g.transport if g is not None else None
+        passive = self.graph.is_passive()
+        recv = None           # polled receive of the partner's snapshot
+        send = None           # (request, snapshot) of our own
+        t_round = time.time()
         while not self._stop.is_set():
             if not self.gossip_enable_flag.wait(timeout=0.05):
                 continue
@@ -360,17 +370,28 @@ class BilatGossipDataParallel(Module):
             if alone:
                 time.sleep(self._poll)
                 continue
-            bt = time.time()
-            with self.gossip_lock:
-                out_msg = self.gossip_flat.clone()
-            in_msg, completed = self.gossiper.mix(out_msg)
-            if completed is not False:
-                with self.gossip_lock:
-                    self.gossip_flat.add_(in_msg.to(self.gossip_flat.device)).mul_(0.5)
-                self.rounds_completed += 1
-                self.gossip_meter.update(time.time() - bt)
-            else:
+            if recv is None:
+                t_round = time.time()
+                recv = tr.post_polled_recv(g.in_msg_buffer, g.in_edges[0])
+                if not passive:
+                    with self.gossip_lock:
+                        snap = self.gossip_flat.clone()
+                    send = (tr.post_sends([snap], [g.out_edges[0]])[0], snap)
+            if not recv.is_completed():
                 time.sleep(self._poll)
+                continue
+            recv.wait()
+            if send is None:          # passive: answer now that the partner showed up
+                with self.gossip_lock:
+                    snap = self.gossip_flat.clone()
+                send = (tr.post_sends([snap], [g.out_edges[0]])[0], snap)
+            with self.gossip_lock:
+                self.gossip_flat.add_(g.in_msg_buffer.to(self.gossip_flat.device)).mul_(0.5)
+            send[0].wait()
+            recv, send = None, None
+            g.refresh_peers_()
+            self.rounds_completed += 1
+            self.gossip_meter.update(time.time() - t_round)
 
     # ------------------------------------------------------------------ #
     def __register_hooks(self):

@@ -194,3 +194,91 @@ def test_graphed_trainer_equals_eager(algo):
                                    rtol=1e-4, atol=1e-5)
         assert graphed[r][2] == eager[r][2] == steps
         assert all(l == l for l in graphed[r][1])
+
+
+# --------------------------------------------------------------------------- #
+# AD-PSGD: device-side bilateral handshake
+# --------------------------------------------------------------------------- #
+def _adpsgd_consensus(rank, world, seconds):
+    import time
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel
+    dev = torch.device('cuda', rank)
+    net = torch.nn.Linear(64, 64).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.fill_(float(rank))
+    model = BilatGossipDataParallel(net, rank=rank, world_size=world,
+                                    graph_class=sgp.DynamicBipartiteExponentialGraph,
+                                    mixing_class=sgp.UniformMixing, lr=0.0, momentum=0.0,
+                                    weight_decay=0.0, nesterov=False, verbose=False,
+                                    heartbeat_timeout=20)
+    assert model.transport == 'nvlink'
+    total0 = torch.tensor([float(rank)], device=dev)
+    dist.all_reduce(total0)
+    model.enable_gossip()
+    t0 = time.time()
+    while time.time() - t0 < seconds and model.rounds_completed < 16:
+        time.sleep(0.005)
+    model.disable_gossip()
+    time.sleep(0.3)
+    dist.barrier()
+    model.sync_comms()
+    model._check()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    rounds = model.rounds_completed
+    model.shutdown()
+    return flat.mean().item(), (flat.max() - flat.min()).item(), rounds
+
+
+def test_adpsgd_device_handshake_consensus():
+    n = min(_ngpu(), 4)
+    n = n if n % 2 == 0 else n - 1
+    out = run_distributed(_adpsgd_consensus, n, 30.0, backend='nccl', timeout=300)
+    assert min(o[2] for o in out) >= 2, out
+    assert all(o[1] < 1e-6 for o in out)
+    vals = [o[0] for o in out]
+    assert max(vals) - min(vals) < 0.6 * (n - 1) + 1e-6, vals    # contracted
+    assert min(vals) >= -1e-6 and max(vals) <= n - 1 + 1e-6
+
+
+def _adpsgd_train(rank, world, steps):
+    import time
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 1)).to(dev)
+    model = BilatGossipDataParallel(net, rank=rank, world_size=world,
+                                    graph_class=sgp.DynamicBipartiteExponentialGraph,
+                                    mixing_class=sgp.UniformMixing, lr=0.05, momentum=0.9,
+                                    weight_decay=0.0, nesterov=True, verbose=False,
+                                    heartbeat_timeout=20)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+    g = torch.Generator().manual_seed(rank)
+    w_true = (torch.arange(6.) / 6).to(dev)
+    model.train()
+    model.enable_gossip()
+    losses = []
+    for s in range(steps):
+        x = torch.randn(64, 6, generator=g).to(dev)
+        y = (x @ w_true).unsqueeze(1)
+        loss = ((model(x) - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        losses.append(loss.item())
+    model.eval()
+    model.disable_gossip()
+    applied, rounds = model.grads_applied, model.rounds_completed
+    dist.barrier()
+    model._check()
+    model.shutdown()
+    return losses[0], sum(losses[-5:]) / 5, applied, rounds
+
+
+def test_adpsgd_trains_on_gpu():
+    out = run_distributed(_adpsgd_train, 2, 80, backend='nccl', timeout=300)
+    for first, last, applied, rounds in out:
+        assert last < 0.5 * first, (first, last)
+        assert applied >= 70
