@@ -42,8 +42,10 @@ def parse():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--algo', default='sgp', choices=['sgp', 'osgp', 'dpsgd', 'ar'])
-    ap.add_argument('--batch-size', '--batch_size', dest='batch_size', type=int, default=32,
-                    help='per-GPU batch (reference: 256 per 8-GPU node = 32 per GPU)')
+    ap.add_argument('--batch-size', '--batch_size', dest='batch_size', type=int, default=256,
+                    help='per-agent batch; 256 = every shipped job script of the reference '
+                         '(job_scripts/submit_*.sh: --batch_size 256 per gossip agent); one agent '
+                         'per B200 here')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--model', default='resnet50')
     ap.add_argument('--ppi', type=int, default=1)

@@ -27,8 +27,11 @@ import torch.nn.functional as F
 from . import native
 
 
+FORCE_REFERENCE = False      # debugging / A-B switch: route everything to the PyTorch composition
+
+
 def _can_fuse(x: torch.Tensor) -> bool:
-    if not x.is_cuda or not native.available():
+    if FORCE_REFERENCE or not x.is_cuda or not native.available():
         return False
     return bool(native.load().bn_can_fuse(x))
 
@@ -138,6 +141,7 @@ class MaxPool2dNHWC(nn.MaxPool2d):
         k, s, p = self.kernel_size, self.stride, self.padding
         simple = all(isinstance(v, int) for v in (k, s, p)) and self.dilation == 1 \
             and not self.ceil_mode and not self.return_indices
-        if simple and x.is_cuda and native.available() and native.load().pool_can_fuse(x, k, s, p):
+        if simple and not FORCE_REFERENCE and x.is_cuda and native.available() \
+                and native.load().pool_can_fuse(x, k, s, p):
             return _MaxPoolNHWC.apply(x, k, s, p)
         return super().forward(x)
