@@ -14,7 +14,7 @@ What is different underneath:
 * The reference emulates point-to-point with ``dist.broadcast`` inside one
   2-rank process group per edge.  Here a gossiper owns a *transport*:
 
-  - ``PeerMemoryTransport`` (CUDA, ``ops/peer_mix.py``): the message lives in
+  - ``PeerMemoryTransport`` (CUDA, engine in ``ops/peer_mix.py``): the message lives in
     NVSwitch-mapped symmetric memory and ``mix`` is ONE sm_100a kernel that
     publishes the message, waits on the in-neighbours' sequence flags and
     accumulates their buffers with weighted 16-byte P2P loads.  No NCCL.
@@ -99,6 +99,74 @@ class _PolledRecv(object):
             raise self._err
 
 
+class PeerMemoryTransport(object):
+    """sm_100a data plane for STAND-ALONE gossipers (``README.md:67-68`` of the
+    reference uses ``PushSum``/``PushPull`` directly on a tensor): the message is
+    staged into a chunk-padded buffer whose outbox lives in NVSwitch peer-mapped
+    memory and ``mix`` becomes kernel launches of :class:`~.ops.peer_mix.GossipEngine`
+    -- ``residual=False`` -> the fused publish+pull+mix kernel, ``residual=True`` ->
+    publish + gather (sum of the in-neighbours' weighted messages).  Collective
+    construction (every rank of the world builds its gossiper)."""
+
+    name = 'nvlink'
+
+    def __init__(self, world=None, timeout_s=60.0, grid=None):
+        self.world = world
+        self.timeout_s = timeout_s
+        self.grid = grid
+        self.engine = None
+
+    def bind(self, gossiper, msg):
+        from .ops.peer_mix import GossipEngine, build_tables
+        from .ops import native
+        C = native.load()
+        assert msg.is_cuda and msg.dtype == torch.float32, 'nvlink transport: fp32 CUDA messages'
+        n = msg.numel()
+        self.n = n
+        padded = (n + C.CHUNK - 1) // C.CHUNK * C.CHUNK
+        self.z = torch.zeros(padded, dtype=torch.float32, device=msg.device)
+        world = self.world
+        if world is None:
+            from .parallel.symmetric import LocalWorld, SymmetricWorld
+            if gossiper.world_size > 1:
+                world = SymmetricWorld(msg.device)
+            else:
+                world = LocalWorld(1, [msg.device.index]).view(0)
+        graph, mixing = gossiper._graph_manager, gossiper._mixing_manager
+        self.engine = GossipEngine(world, self.z, graph, mixing, with_residual=True,
+                                   timeout_s=self.timeout_s, grid=self.grid, name='gossiper')
+        # residual=True exchanges are summed with unit edge weights (the caller
+        # already scaled by lo; reference 'uniform' weight == 1, mixing_manager.py:47)
+        table, wtable = build_tables(graph, mixing, msg.device)
+        unit = wtable.clone()
+        unit[:, 1:] = (wtable[:, 1:] != 0).float()
+        self._tables = (table, wtable)
+        self._unit_tables = (table, unit)
+
+    def mix(self, gossiper, out_msg, ps_weight, residual):
+        e = self.engine
+        w = float(ps_weight.reshape(-1)[0]) if torch.is_tensor(ps_weight) else float(ps_weight)
+        self.z[:self.n].copy_(out_msg.reshape(-1))
+        e.ps_weight = w
+        if residual:
+            e.ctx.set_schedule(*self._unit_tables)
+            e.publish(sgd=False, fold=False, in_numerator=True)
+            e.gather()
+            msg = e.residual[:self.n]
+            psw = torch.full((1,), e.res_weight, dtype=out_msg.dtype, device=out_msg.device)
+            e.ps_weight = w                          # publish keeps only the self-loop share
+        else:
+            e.ctx.set_schedule(*self._tables)
+            e.mix(sgd=False, in_numerator=True)      # z <- xn / wn
+            wn = e.ps_weight
+            msg = self.z[:self.n] * wn               # numerator, like the c10d path
+            psw = torch.full((1,), wn, dtype=out_msg.dtype, device=out_msg.device)
+        e.check()
+        e.sync_graph()
+        gossiper.refresh_peers_(rotate=False)
+        return msg, psw
+
+
 # --------------------------------------------------------------------------- #
 # base class
 # --------------------------------------------------------------------------- #
@@ -143,7 +211,11 @@ class Gossiper(object):
         self.placeholder = self.in_msg_buffer.clone()
         self._extra_placeholders = []
         self._pending_req = None
+        if transport == 'nvlink':
+            transport = PeerMemoryTransport()
         self.transport = transport if transport is not None else C10dTransport()
+        if isinstance(self.transport, PeerMemoryTransport):
+            self.transport.bind(self, msg)
 
     # -- properties --------------------------------------------------------- #
     @property
@@ -278,6 +350,8 @@ class PushSum(Gossiper):
         if self.logger is not None:
             self.logger.debug('in/out -peers {}/{}'.format(
                 self.in_edges, self.out_edges))
+        if isinstance(self.transport, PeerMemoryTransport):
+            return self.transport.mix(self, out_msg, ps_weight, residual)
         return self._exchange(out_msg, ps_weight, residual)
 
 
@@ -288,6 +362,8 @@ class PushPull(Gossiper):
         if self.logger is not None:
             self.logger.debug('in/out -peers {}/{}'.format(
                 self.in_edges, self.out_edges))
+        if isinstance(self.transport, PeerMemoryTransport):
+            return self.transport.mix(self, out_msg, ps_weight, residual)
         return self._exchange(out_msg, ps_weight, residual)
 
 

@@ -296,6 +296,7 @@ class GossipDataParallel(Module):
         self.lazy_mixing = (not self.asynch and mixing.is_regular() and not self.overlap)
         self.lazy_ps_factor = self.gossip_ps_factor.clone()
         self._w = 1.0                      # c10d transport: python mirror of ps_weight
+        self._rounds_started = 0
         self._fused_optimizer = None
 
         if on_cuda and not self.__cpu_comm and use_streams:
@@ -396,6 +397,8 @@ class GossipDataParallel(Module):
 
     def state_dict(self, finish_gossip=True, *args, **kwargs):
         if finish_gossip:
+            if self.asynch:
+                self._drain_async()
             self._query_gossip_queue()
             self._flush_pending()
         super_dict = super(GossipDataParallel, self).state_dict(*args, **kwargs)
@@ -518,8 +521,40 @@ class GossipDataParallel(Module):
             dist.barrier()
 
     def sync_comms(self):
+        if self.asynch:
+            self._drain_async()
         self._query_gossip_queue(non_blocking=False)
         self._flush_pending()
+
+    def _drain_async(self):
+        """Collective drain for bounded-staleness runs, where ranks start different
+        numbers of gossip rounds.  (1) Until EVERY rank has left its training loop
+        (async barrier) keep serving: finish rounds non-blockingly and start
+        gossip-only rounds, so a peer that is still inside a forced wait gets the
+        message it needs.  (2) Agree on the furthest round anybody started and
+        catch up to it; only then is a blocking drain safe.  The reference relies
+        on its 300 s heartbeat in this situation."""
+        if not (dist.is_initialized() and self.is_local_master and self.gossip_enable):
+            return
+        dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+        flag = torch.zeros(1, device=dev)
+        left_loop = dist.all_reduce(flag, async_op=True)
+        t0 = time.time()
+        while not left_loop.is_completed():
+            if self._query_gossip_queue(non_blocking=True) is not False or not self.gossiping:
+                self.transfer_params()
+            time.sleep(0.0005)
+            if time.time() - t0 > self._timeout_s:
+                raise NameError('Gossip flag timeout')
+        left_loop.wait()
+        t = torch.tensor([self._rounds_started], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        target = int(t.item())
+        while True:
+            self._query_gossip_queue(non_blocking=False)
+            if self._rounds_started >= target:
+                break
+            self.transfer_params()
 
     # -- gossip state machine ------------------------------------------------ #
     def _query_gossip_queue(self, non_blocking=False):
@@ -573,6 +608,7 @@ class GossipDataParallel(Module):
             self._w *= self_w
         self.params_mixed = False
         self.gossiping = True
+        self._rounds_started += 1
         return True
 
     def _launch_kernel_gossip(self):

@@ -190,3 +190,61 @@ def test_update_gossiper_peers_per_itr_and_consensus():
     mean = sum(_flat(_model(r)) for r in range(world)) / world
     for r in range(world):
         torch.testing.assert_close(torch.tensor(out[r]), mean, rtol=0, atol=2e-3)
+
+
+def _async_worker(rank, world, synch_freq, steps):
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world)
+    model = GossipDataParallel(_model(rank), graph=graph, overlap=True, synch_freq=synch_freq,
+                               rank=rank, world_size=world)
+    assert model.asynch and not model.lazy_mixing
+    x = torch.zeros(2, 6)
+    for _ in range(steps):
+        model(x)                       # pre-forward hook: poll / fold / launch next gossip
+        assert model.num_updates <= synch_freq
+    model.sync_comms()
+    model.unbias()
+    return _flat(model.module).tolist(), float(model.ps_weight)
+
+
+def test_bounded_staleness_conserves_mass_and_mixes():
+    world = 4
+    out = run_distributed(_async_worker, world, 2, 12)
+    x0 = torch.stack([_flat(_model(r)) for r in range(world)])
+    # sum_i w_i z_i == sum_i x_i(0): push-sum mass is conserved without gradients
+    mass = sum(torch.tensor(z) * w for z, w in out)
+    torch.testing.assert_close(mass, x0.sum(0), rtol=1e-4, atol=1e-4)
+    assert abs(sum(w for _, w in out) - world) < 1e-4
+    spread0 = (x0 - x0.mean(0)).abs().max().item()
+    zs = torch.stack([torch.tensor(z) for z, _ in out])
+    assert (zs - zs.mean(0)).abs().max().item() < 0.2 * spread0
+
+
+def _hier_worker(rank, world, steps):
+    """2 nodes x 2 processes: only node masters gossip; locals mirror them."""
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    torch.manual_seed(rank)
+    model = GossipDataParallel(_model(rank), nprocs_per_node=2, rank=rank, world_size=world)
+    assert model.dist_config['world_size'] == 2 and model.dist_config['rank'] == rank // 2
+    assert model.is_local_master == (rank % 2 == 0)
+    opt = torch.optim.SGD(model.parameters(), lr=LR)
+    for step in range(steps):
+        x, y = _batch(rank, step)
+        ((model(x) - y) ** 2).mean().backward()
+        opt.step()
+        opt.zero_grad()
+        model.transfer_params()
+    model.sync_comms()
+    model.unbias()
+    x, _ = _batch(0, 99)
+    model(x)                           # forward re-broadcasts the master's parameters
+    return _flat(model.module).tolist(), [p.grad is None for p in model.parameters()]
+
+
+def test_hierarchical_nprocs_per_node():
+    out = run_distributed(_hier_worker, 4, 3)
+    p = [torch.tensor(o[0]) for o in out]
+    torch.testing.assert_close(p[0], p[1], rtol=0, atol=0)      # same node -> identical
+    torch.testing.assert_close(p[2], p[3], rtol=0, atol=0)
+    # two nodes on a 1-peer graph average exactly at every mix
+    torch.testing.assert_close(p[0], p[2], rtol=1e-5, atol=1e-6)

@@ -282,3 +282,40 @@ def test_adpsgd_trains_on_gpu():
     for first, last, applied, rounds in out:
         assert last < 0.5 * first, (first, last)
         assert applied >= 70
+
+
+# --------------------------------------------------------------------------- #
+# stand-alone gossipers on the nvlink transport (README usage of the reference)
+# --------------------------------------------------------------------------- #
+def _standalone_pushsum(rank, world, residual):
+    from stochastic_gradient_push_b200.gossiper import PushSum
+    dev = torch.device('cuda', rank)
+    graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world)
+    x = torch.full((5000,), 10.0 * rank, device=dev)
+    g = PushSum(x, graph, rank=rank, world_size=world, transport='nvlink')
+    w = torch.ones(1, device=dev)
+    trace = []
+    for _ in range(3):
+        if residual:
+            lo = 1.0 / (len(g.out_edges) + 1)
+            x, w = x * lo, w * lo
+            r, wr = g.mix(x.clone(), w, residual=True)
+            x, w = x + r, w + wr
+        else:
+            x, w = g.mix(x.clone(), w, residual=False)
+            x, w = x.clone(), w.clone()
+        trace.append(round(x[0].item(), 3))
+    assert abs(float(w) - 1.0) < 1e-5
+    return trace
+
+
+@pytest.mark.parametrize('residual', [False, True])
+def test_standalone_pushsum_on_peer_memory(residual):
+    n = 4 if _ngpu() >= 4 else 2
+    out = run_distributed(_standalone_pushsum, n, residual, backend='nccl', timeout=300)
+    if n == 4:
+        want = {0: [15, 15, 15], 1: [5, 15, 15], 2: [15, 15, 15], 3: [25, 15, 15]}
+    else:
+        want = {0: [5, 5, 5], 1: [5, 5, 5]}
+    for r in range(n):
+        assert out[r] == want[r], out
