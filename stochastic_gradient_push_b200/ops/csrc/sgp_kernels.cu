@@ -375,8 +375,24 @@ __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // may outbox[step&1] be overwritten?  (the publish kernel would otherwise
+        // spin on these acks; the host checks first so no kernel ever waits)
+        uint32_t acks_ok = 1u;
+        if (step >= st->ack_from + 2u) {
+            RowInfo prev;
+            load_row(a, step - 2u, prev);
+            for (int k = 0; k < prev.n_out; ++k) {
+                const int o = prev.out[k];
+                if (o < 0 || o == a.rank) continue;
+                if ((int32_t)(ld_acquire_sys(&a.pads[a.rank]->ack_seq[o]) - (step - 1u)) < 0)
+                    acks_ok = 0u;
+            }
+        }
         st->bilat_done = (uint32_t)s_all;
-        if (host_flag) *((volatile uint32_t*)host_flag) = (uint32_t)s_all;
+        if (host_flag) {
+            ((volatile uint32_t*)host_flag)[0] = (uint32_t)s_all;
+            ((volatile uint32_t*)host_flag)[1] = acks_ok;
+        }
         __threadfence_system();
     }
 }

@@ -328,14 +328,13 @@ class BilatGossipDataParallel(Module):
                 time.sleep(self._poll)
                 continue
             bt = time.time()
-            if not published and not passive:
-                with self.gossip_lock:
-                    e.publish_only()
-                published = True
             e.probe(self._host_flag)
             self.gossip_stream.synchronize()
-            ready = int(self._host_flag[0]) == 1
-            if ready and not published:          # passive: answer once the partner showed up
+            ready = int(self._host_flag[0]) == 1        # partner's snapshot is visible
+            may_publish = int(self._host_flag[1]) == 1  # our outbox buffer has been released
+            # active ranks publish unconditionally, passive ranks only once their
+            # partner showed up; never before the readers of round r-2 have acked
+            if not published and may_publish and (ready or not passive):
                 with self.gossip_lock:
                     e.publish_only()
                 published = True
@@ -351,18 +350,37 @@ class BilatGossipDataParallel(Module):
                 time.sleep(self._poll)
 
     def _loop_c10d(self):
-        """Same protocol over isend/irecv.  Neither role ever blocks the loop:
-        a rank whose partner has gone quiet (finished, validating, slow) keeps
-        applying its own gradients -- the reference's active rank blocks inside
-        ``mix`` here (``gossip/gossiper.py:290-299``)."""
+        """Same protocol over isend/irecv.  "Has my partner published?" is a key in
+        the c10d store (the analogue of the probe kernel): a receive is only posted
+        once the matching send exists, so no rank ever blocks on -- or exits with --
+        a dangling receive, whatever its partner is doing (finished, validating,
+        slow).  The reference's active rank blocks inside ``mix`` here
+        (``gossip/gossiper.py:290-299``)."""
         cfg = dict(self.dist_config)
         alone = self.gossiper is None
         g = self.gossiper
         tr = g.transport if g is not None else None
         passive = self.graph.is_passive()
-        recv = None           # polled receive of the partner's snapshot
-        send = None           # (request, snapshot) of our own
+        store = None
+        if not alone:
+            from torch.distributed.distributed_c10d import _get_default_store
+            store = _get_default_store()
+        rnd = 0
+        sent = None
+        inflight = []
         t_round = time.time()
+
+        def key(r, src, dst):
+            return 'adpsgd/%d/%d>%d' % (r, src, dst)
+
+        def publish():
+            with self.gossip_lock:
+                snap = self.gossip_flat.clone()
+            out = g.out_edges[0]
+            req = tr.post_sends([snap], [out])[0]
+            store.set(key(rnd, out.src, out.dest), '1')
+            return (req, snap)
+
         while not self._stop.is_set():
             if not self.gossip_enable_flag.wait(timeout=0.05):
                 continue
@@ -370,26 +388,28 @@ class BilatGossipDataParallel(Module):
             if alone:
                 time.sleep(self._poll)
                 continue
-            if recv is None:
+            if sent is None:
                 t_round = time.time()
-                recv = tr.post_polled_recv(g.in_msg_buffer, g.in_edges[0])
                 if not passive:
-                    with self.gossip_lock:
-                        snap = self.gossip_flat.clone()
-                    send = (tr.post_sends([snap], [g.out_edges[0]])[0], snap)
-            if not recv.is_completed():
+                    sent = publish()
+            in_edge = g.in_edges[0]
+            if not store.check([key(rnd, in_edge.src, in_edge.dest)]):
                 time.sleep(self._poll)
                 continue
-            recv.wait()
-            if send is None:          # passive: answer now that the partner showed up
-                with self.gossip_lock:
-                    snap = self.gossip_flat.clone()
-                send = (tr.post_sends([snap], [g.out_edges[0]])[0], snap)
+            if sent is None:          # passive: answer now that the partner showed up
+                sent = publish()
+            tr.post_recvs([g.in_msg_buffer], [in_edge])[0].wait()
             with self.gossip_lock:
                 self.gossip_flat.add_(g.in_msg_buffer.to(self.gossip_flat.device)).mul_(0.5)
-            send[0].wait()
-            recv, send = None, None
+            # never block on OUR send: the partner may have gone quiet before
+            # posting its receive.  A send is certainly complete once the partner
+            # has answered two later rounds, so only those are reaped.
+            inflight.append(sent)
+            while len(inflight) > 2:
+                inflight.pop(0)[0].wait()
+            sent = None
             g.refresh_peers_()
+            rnd += 1
             self.rounds_completed += 1
             self.gossip_meter.update(time.time() - t_round)
 

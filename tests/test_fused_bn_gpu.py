@@ -110,40 +110,51 @@ def test_resnet50_eval_matches_torchvision():
     assert (yo - yt).abs().max().item() < 2e-3 * scale
 
 
-def test_resnet50_fused_vs_unfused_training_step():
-    """Same network object, fused kernels vs the PyTorch composition.  Batch
-    statistics over tiny late-stage feature maps amplify rounding noise, so the
-    comparison is relative to the tensor scale, on a training-sized input."""
+@pytest.mark.parametrize('amp', [False, True])
+def test_resnet50_every_bn_layer_matches_composition(amp):
+    """Per-layer A/B inside a real ResNet-50 pass: every FusedBatchNormAct2d call
+    is compared with the PyTorch composition on the SAME input and the SAME upstream
+    gradient.  (Comparing two whole networks end to end is meaningless here: batch
+    statistics over the tiny late-stage feature maps amplify rounding noise
+    chaotically; measured per-layer agreement is ~1e-7 in fp32.)"""
     from stochastic_gradient_push_b200.models import resnet50
-    from stochastic_gradient_push_b200.ops import fused_bn
     torch.manual_seed(0)
     net = resnet50().cuda().to(memory_format=torch.channels_last)
     x = torch.randn(16, 3, 128, 128, device='cuda').contiguous(memory_format=torch.channels_last)
-    state = {k: v.clone() for k, v in net.state_dict().items()}
+    rows = []
+    orig = FusedBatchNormAct2d.forward
 
-    def run(force_ref):
-        net.load_state_dict(state)
-        net.zero_grad(set_to_none=True)
-        fused_bn.FORCE_REFERENCE = force_ref
-        try:
-            y = net(x)
-            y.square().mean().backward()
-        finally:
-            fused_bn.FORCE_REFERENCE = False
-        return y.detach().clone(), [p.grad.detach().clone() for p in net.parameters()]
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    def patched(self, inp, residual=None, relu=False):
+        with torch.enable_grad():
+            xs = [inp.detach().clone().requires_grad_(True) for _ in range(2)]
+            rs = [None if residual is None else residual.detach().clone().requires_grad_(True)
+                  for _ in range(2)]
+            ws = [self.weight.detach().clone().requires_grad_(True) for _ in range(2)]
+            bs = [self.bias.detach().clone().requires_grad_(True) for _ in range(2)]
+            assert _can_fuse(inp)
+            y0 = fused_bn_act(xs[0], ws[0], bs[0], None, None, None, residual=rs[0], relu=relu)
+            y1 = reference_bn_act(xs[1].float(), ws[1], bs[1], None, None, None,
+                                  residual=None if rs[1] is None else rs[1].float(), relu=relu)
+            g = torch.randn_like(y1)
+            y0.backward(g.to(y0.dtype))
+            y1.backward(g)
+            rows.append((rel(y0, y1), rel(xs[0].grad, xs[1].grad), rel(ws[0].grad, ws[1].grad),
+                         rel(bs[0].grad, bs[1].grad)))
+        return orig(self, inp, residual, relu)
+
+    FusedBatchNormAct2d.forward = patched
     try:
-        y_ref, g_ref = run(True)
-        y_fus, g_fus = run(False)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            net(x)
     finally:
-        torch.backends.cudnn.allow_tf32 = True
-    scale = y_ref.abs().max().item()
-    assert (y_fus - y_ref).abs().max().item() < 5e-3 * scale
-    num = sum((a - b).float().pow(2).sum().item() for a, b in zip(g_fus, g_ref)) ** 0.5
-    den = sum(b.float().pow(2).sum().item() for b in g_ref) ** 0.5
-    assert num / den < 2e-2, num / den
+        FusedBatchNormAct2d.forward = orig
+    assert len(rows) == 53
+    tol_y, tol_g = (1e-2, 2e-2) if amp else (1e-5, 5e-3)     # dx tolerates a rare ReLU-mask flip
+    for ry, rdx, rdw, rdb in rows:
+        assert ry < tol_y and rdx < tol_g and rdw < tol_g and rdb < tol_g, (ry, rdx, rdw, rdb)
 
 
 @pytest.mark.parametrize('shape,k,s,p', [((4, 64, 28, 28), 3, 2, 1), ((2, 16, 9, 11), 3, 2, 1),
