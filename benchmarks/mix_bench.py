@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--grid', type=int, default=None)
     ap.add_argument('--bf16', action='store_true')
+    ap.add_argument('--segments', type=int, default=4)
     ap.add_argument('--mode', default='mix', choices=['mix', 'mix_nosgd', 'publish', 'gather', 'local'])
     args = ap.parse_args()
 
@@ -48,7 +49,8 @@ def main():
     shadow = torch.zeros(n, device=dev, dtype=torch.bfloat16) if args.bf16 else None
     mom = torch.zeros(n, device=dev)
     eng = GossipEngine(sw, z, graph, sgp.UniformMixing(graph, dev), grad=grad, momentum=mom,
-                       shadow=shadow, with_residual=True, grid=args.grid, timeout_s=20.0)
+                       shadow=shadow, with_residual=True, grid=args.grid, timeout_s=20.0,
+                       segments=args.segments)
     eng.set_hyper(1e-3, 0.9, 1e-4, True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -100,7 +102,7 @@ def main():
     nvlink_bytes = n_in * n * 4
     if rank == 0:
         print(json.dumps({'mode': args.mode, 'world': world, 'ppi': args.ppi, 'numel': n,
-                          'grid': eng.grid, 'ms_median': round(med, 4), 'ms_best': round(best, 4),
+                          'grid': eng.grid, 'segments': args.segments, 'ms_median': round(med, 4), 'ms_best': round(best, 4),
                           'nvlink_GBps_per_rank': round(nvlink_bytes / med / 1e6, 1),
                           'bf16': args.bf16}))
     if multi:

@@ -164,6 +164,7 @@ public:
         keep_.push_back(state);
         keep_.push_back(hyper);
         max_grid_ = sgp_max_resident_ctas(device_);
+        args_.segments = 4;
     }
 
     void set_schedule(torch::Tensor table, torch::Tensor wtable)
@@ -248,6 +249,8 @@ public:
     }
 
     void set_timeout(double seconds) { args_.timeout_ns = (unsigned long long)(seconds * 1e9); }
+    void set_segments(int k) { TORCH_CHECK(k >= 1 && k < SGP_SEQ_STRIDE); args_.segments = k; }
+    int segments() const { return args_.segments; }
 
 private:
     SgpArgs prepare(unsigned int flags) const
@@ -355,6 +358,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("set_grad", &GossipContext::set_grad)
         .def("set_sgd_buffers", &GossipContext::set_sgd_buffers)
         .def("set_timeout", &GossipContext::set_timeout)
+        .def("set_segments", &GossipContext::set_segments)
+        .def("segments", &GossipContext::segments)
         .def("max_grid", &GossipContext::max_grid)
         .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))
         .def("gather", &GossipContext::gather, py::arg("grid"), py::arg("pub_grid"))

@@ -25,6 +25,7 @@
 #define SGP_CHUNK       (SGP_THREADS * SGP_VEC * SGP_UNROLL)   // 4096 elements
 #define SGP_TABLE_ROW   (2 + 2 * SGP_MAX_PEERS)                // n_in,n_out,in[8],out[8]
 #define SGP_WTABLE_ROW  (1 + SGP_MAX_PEERS)                    // self_w, in_w[8]
+#define SGP_SEQ_STRIDE  16     // pub_seq = step * 16 + segments_published  (<= 15 segments)
 
 // status codes written to SgpState::status (0 == healthy)
 #define SGP_OK               0
@@ -34,7 +35,8 @@
 
 // ---- symmetric (peer-visible) per-rank signal pad --------------------------
 struct __align__(128) SgpSignalPad {
-    // pub_seq[b] == s+1  <=>  CTA b's share of outbox[s&1] for step s is visible
+    // pub_seq[b] == s*SGP_SEQ_STRIDE + k  <=>  the first k segments of CTA b's share of
+    // outbox[s&1] for step s are visible (k == segments: all of it)
     uint32_t pub_seq[SGP_MAX_CTAS];
     // ack_seq[r] == s+1  <=>  rank r finished reading our outbox of step s
     uint32_t ack_seq[SGP_MAX_RANKS];
@@ -111,6 +113,7 @@ struct SgpArgs {
     const SgpHyper*      hyper;
     unsigned long long   timeout_ns;
     unsigned int         flags;
+    int                  segments;   // phase-1/phase-2 interleave granularity per CTA
 };
 
 #ifdef __CUDACC__

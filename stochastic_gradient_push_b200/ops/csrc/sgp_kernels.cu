@@ -104,162 +104,182 @@ sgp_step_kernel(const SgpArgs a)
     const uint64_t pol_last = l2_evict_last_policy();
     const bool do_sgd = (flags & SGP_F_SGD) && (hp.do_sgd != 0.f);
 
-    // ---------------- phase 1: local update + publish ----------------------
-    if (flags & SGP_F_PHASE1) {
-        if ((flags & SGP_F_PUBLISH) && step >= st->ack_from + 2u) {
-            // WAR fence: outbox[parity] was last read at step-2 by that step's
-            // out-neighbours; wait for their acks before overwriting it.
-            if (tid == 0) {
-                RowInfo prev;
-                load_row(a, step - 2u, prev);
-                int ok = 1;
-                for (int k = 0; k < prev.n_out; ++k) {
-                    const int o = prev.out[k];
-                    if (o == a.rank || o < 0) continue;
-                    ok &= spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns,
-                                        SGP_ERR_TIMEOUT_ACK) ? 1 : 0;
-                }
-                s_ok = ok;
-            }
-            __syncthreads();
-        }
+    // Work decomposition: this CTA owns chunks b, b+G, b+2G, ...; they are cut into
+    // K contiguous SEGMENTS.  For each segment the CTA runs phase 1 (local update +
+    // publish, HBM-bound), releases a per-CTA progress counter
+    //        pub_seq[b] = step * SGP_SEQ_STRIDE + seg + 1
+    // and immediately runs phase 2 (pull + mix, NVLink-bound) on the same segment.
+    // CTAs sharing an SM drift apart, so one CTA's NVLink phase overlaps another's
+    // HBM phase and the kernel approaches max(HBM time, NVLink time) instead of
+    // their sum; the own-term re-read of phase 2 always hits L2.
+    const long long my_chunks = (nchunks > b) ? (nchunks - 1 - b) / gridDim.x + 1 : 0;
+    int K = a.segments < 1 ? 1 : a.segments;
+    if (K > SGP_SEQ_STRIDE - 1) K = SGP_SEQ_STRIDE - 1;
+    const uint32_t seq_base = step * (uint32_t)SGP_SEQ_STRIDE;
 
-        const float inv_w1 = 1.f / w1;
-        const bool write_z = !(flags & SGP_F_PHASE2) && !(flags & SGP_F_KEEP_Z);
-
-        for (long long c = b; c < nchunks; c += gridDim.x) {
-            const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
-            float4 x[SGP_UNROLL], g[SGP_UNROLL], m[SGP_UNROLL], r[SGP_UNROLL];
-#pragma unroll
-            for (int u = 0; u < SGP_UNROLL; ++u) {
-                const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                x[u] = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
-                if (do_sgd) {
-                    if (flags & SGP_F_GRAD_BF16)
-                        g[u] = bf16x4_to_f4(ld_once_u2(reinterpret_cast<const uint2*>(
-                                   reinterpret_cast<const __nv_bfloat16*>(a.g) + i), pol_first));
-                    else
-                        g[u] = ld_once_f4(reinterpret_cast<const float4*>(
-                                   reinterpret_cast<const float*>(a.g) + i), pol_first);
-                    m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
-                }
-                if (flags & SGP_F_FOLD_RES)
-                    r[u] = ld_once_f4(reinterpret_cast<const float4*>(a.residual + i), pol_first);
-            }
-#pragma unroll
-            for (int u = 0; u < SGP_UNROLL; ++u) {
-                const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                float4 xv = mul4(x[u], wmul);               // numerator (exact if w == 1)
-                if (do_sgd) {
-                    float4 gv = mul4(g[u], hp.grad_scale);
-                    float4 mv = m[u];
-                    sgd1(xv.x, gv.x, mv.x, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
-                    sgd1(xv.y, gv.y, mv.y, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
-                    sgd1(xv.z, gv.z, mv.z, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
-                    sgd1(xv.w, gv.w, mv.w, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
-                    st_f4(reinterpret_cast<float4*>(a.m + i), mv);
-                    if (flags & SGP_F_ZERO_GRAD) {
-                        if (flags & SGP_F_GRAD_BF16)
-                            st_u2(reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.g) + i),
-                                  make_uint2(0u, 0u));
-                        else
-                            st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g) + i),
-                                  make_float4(0.f, 0.f, 0.f, 0.f));
-                    }
-                }
-                if (flags & SGP_F_FOLD_RES) {
-                    xv.x += r[u].x; xv.y += r[u].y; xv.z += r[u].z; xv.w += r[u].w;
-                }
-                if (flags & SGP_F_PUBLISH)   // keep the outbox in L2 for phase 2 / peers
-                    st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
-                if (write_z) {
-                    const float4 zv = mul4(xv, inv_w1);
-                    st_f4(reinterpret_cast<float4*>(a.z + i), zv);
-                    if (flags & SGP_F_SHADOW)
-                        st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
-                }
-            }
-        }
-
-        if (flags & SGP_F_PUBLISH) {
-            __syncthreads();
-            if (tid == 0) {
-                st_relaxed_sys_f32(&mypad->psw[parity], w1);   // same value from every CTA
-                __threadfence_system();
-                st_release_sys(&mypad->pub_seq[b], step + 1u);
-            }
-        }
-    }
-
-    // overlap publish keeps the self-loop share locally (w <- self_w * w1); a
-    // snapshot-only publish (AD-PSGD) leaves the weight alone
-    float w_next = ((flags & SGP_F_PUBLISH) && !(flags & SGP_F_KEEP_Z)) ? row.self_w * w1 : w1;
-
-    // ---------------- phase 2: pull + mix ----------------------------------
-    if (flags & SGP_F_PHASE2) {
+    if ((flags & SGP_F_PHASE1) && (flags & SGP_F_PUBLISH) && step >= st->ack_from + 2u) {
+        // WAR fence: outbox[parity] was last read at step-2 by that step's
+        // out-neighbours; wait for their acks before overwriting it.
         if (tid == 0) {
+            RowInfo prev;
+            load_row(a, step - 2u, prev);
             int ok = 1;
-            float wn = row.self_w * w1;
-            for (int k = 0; k < row.n_in; ++k) {
-                const int j = row.in[k];
-                if (j < 0) continue;
-                const SgpSignalPad* pj = a.pads[j];
-                ok &= spin_wait_geq(&pj->pub_seq[b], step + 1u, st, a.timeout_ns,
-                                    SGP_ERR_TIMEOUT_PUB) ? 1 : 0;
-                wn = fmaf(row.in_w[k], ld_relaxed_sys_f32(&pj->psw[parity]), wn);
+            for (int k = 0; k < prev.n_out; ++k) {
+                const int o = prev.out[k];
+                if (o == a.rank || o < 0) continue;
+                ok &= spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns,
+                                    SGP_ERR_TIMEOUT_ACK) ? 1 : 0;
             }
-            s_wn = wn;
             s_ok = ok;
         }
         __syncthreads();
-        const float wn = s_wn;
-        w_next = wn;
-        if (s_ok) {
-            const float inv_wn = 1.f / wn;
-            const float* peer_out[SGP_MAX_PEERS];
-#pragma unroll
-            for (int k = 0; k < SGP_MAX_PEERS; ++k)
-                peer_out[k] = (k < row.n_in && row.in[k] >= 0)
-                                  ? a.outboxes[row.in[k]] + (size_t)parity * a.n : nullptr;
+    }
 
-            // reverse order: the chunks this CTA published last are still in L2
-            const long long my_chunks = (nchunks > b) ? (nchunks - 1 - b) / gridDim.x + 1 : 0;
-            for (long long it = my_chunks - 1; it >= 0; --it) {
+    const float inv_w1 = 1.f / w1;
+    const bool write_z = !(flags & SGP_F_PHASE2) && !(flags & SGP_F_KEEP_Z);
+    // overlap publish keeps the self-loop share locally (w <- self_w * w1); a
+    // snapshot-only publish (AD-PSGD) leaves the weight alone
+    float w_next = ((flags & SGP_F_PUBLISH) && !(flags & SGP_F_KEEP_Z)) ? row.self_w * w1 : w1;
+    float inv_wn = 1.f;
+    bool pull_ok = true;
+    const float* peer_out[SGP_MAX_PEERS];
+#pragma unroll
+    for (int k = 0; k < SGP_MAX_PEERS; ++k)
+        peer_out[k] = ((flags & SGP_F_PHASE2) && k < row.n_in && row.in[k] >= 0)
+                          ? a.outboxes[row.in[k]] + (size_t)parity * a.n : nullptr;
+
+    for (int seg = 0; seg < K; ++seg) {
+        const long long it_lo = my_chunks * seg / K;
+        const long long it_hi = my_chunks * (seg + 1) / K;
+
+        // ---------------- phase 1: local update + publish ------------------
+        if (flags & SGP_F_PHASE1) {
+            for (long long it = it_lo; it < it_hi; ++it) {
                 const long long c = b + it * gridDim.x;
                 const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
-                float4 acc[SGP_UNROLL];
-                float4 pv[SGP_UNROLL];
+                float4 x[SGP_UNROLL], g[SGP_UNROLL], m[SGP_UNROLL], r[SGP_UNROLL];
 #pragma unroll
                 for (int u = 0; u < SGP_UNROLL; ++u) {
                     const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                    // own term: the snapshot this CTA published, or (AD-PSGD) the live
-                    // parameters, which may already carry newer local SGD updates
-                    const float* own = (flags & SGP_F_SELF_FROM_Z) ? a.z : my_out;
-                    acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(own + i), pol_first),
-                                  (flags & SGP_F_SELF_FROM_Z) ? row.self_w * w0 : row.self_w);
+                    x[u] = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
+                    if (do_sgd) {
+                        if (flags & SGP_F_GRAD_BF16)
+                            g[u] = bf16x4_to_f4(ld_once_u2(reinterpret_cast<const uint2*>(
+                                       reinterpret_cast<const __nv_bfloat16*>(a.g) + i), pol_first));
+                        else
+                            g[u] = ld_once_f4(reinterpret_cast<const float4*>(
+                                       reinterpret_cast<const float*>(a.g) + i), pol_first);
+                        m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
+                    }
+                    if (flags & SGP_F_FOLD_RES)
+                        r[u] = ld_once_f4(reinterpret_cast<const float4*>(a.residual + i), pol_first);
                 }
-                // peer loads: all UNROLL requests of one peer in flight together
+#pragma unroll
+                for (int u = 0; u < SGP_UNROLL; ++u) {
+                    const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                    float4 xv = mul4(x[u], wmul);               // numerator (exact if w == 1)
+                    if (do_sgd) {
+                        float4 gv = mul4(g[u], hp.grad_scale);
+                        float4 mv = m[u];
+                        sgd1(xv.x, gv.x, mv.x, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                        sgd1(xv.y, gv.y, mv.y, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                        sgd1(xv.z, gv.z, mv.z, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                        sgd1(xv.w, gv.w, mv.w, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                        st_f4(reinterpret_cast<float4*>(a.m + i), mv);
+                        if (flags & SGP_F_ZERO_GRAD) {
+                            if (flags & SGP_F_GRAD_BF16)
+                                st_u2(reinterpret_cast<uint2*>(
+                                          reinterpret_cast<__nv_bfloat16*>(a.g) + i), make_uint2(0u, 0u));
+                            else
+                                st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g) + i),
+                                      make_float4(0.f, 0.f, 0.f, 0.f));
+                        }
+                    }
+                    if (flags & SGP_F_FOLD_RES) {
+                        xv.x += r[u].x; xv.y += r[u].y; xv.z += r[u].z; xv.w += r[u].w;
+                    }
+                    if (flags & SGP_F_PUBLISH)   // keep the outbox in L2 for phase 2 / peers
+                        st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
+                    if (write_z) {
+                        const float4 zv = mul4(xv, inv_w1);
+                        st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                        if (flags & SGP_F_SHADOW)
+                            st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    }
+                }
+            }
+            if (flags & SGP_F_PUBLISH) {
+                __syncthreads();
+                if (tid == 0) {
+                    if (seg == 0) st_relaxed_sys_f32(&mypad->psw[parity], w1);  // same value from every CTA
+                    __threadfence_system();
+                    st_release_sys(&mypad->pub_seq[b], seq_base + (uint32_t)seg + 1u);
+                }
+            }
+        }
+
+        // ---------------- phase 2: pull + mix ------------------------------
+        if (flags & SGP_F_PHASE2) {
+            if (tid == 0) {
+                int ok = 1;
+                float wn = row.self_w * w1;
                 for (int k = 0; k < row.n_in; ++k) {
-                    const float* po = peer_out[k];
-                    if (po == nullptr) continue;
+                    const int j = row.in[k];
+                    if (j < 0) continue;
+                    const SgpSignalPad* pj = a.pads[j];
+                    ok &= spin_wait_geq(&pj->pub_seq[b], seq_base + (uint32_t)seg + 1u, st,
+                                        a.timeout_ns, SGP_ERR_TIMEOUT_PUB) ? 1 : 0;
+                    if (seg == 0) wn = fmaf(row.in_w[k], ld_relaxed_sys_f32(&pj->psw[parity]), wn);
+                }
+                if (seg == 0) s_wn = wn;
+                s_ok = ok;
+            }
+            __syncthreads();
+            if (seg == 0) {
+                w_next = s_wn;
+                inv_wn = 1.f / s_wn;
+            }
+            pull_ok = pull_ok && (s_ok != 0);
+            if (pull_ok) {
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+                    float4 acc[SGP_UNROLL];
+                    float4 pv[SGP_UNROLL];
 #pragma unroll
                     for (int u = 0; u < SGP_UNROLL; ++u) {
                         const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                        pv[u] = ld_stream_f4(reinterpret_cast<const float4*>(po + i));
+                        // own term: the snapshot this CTA just published (L2-resident),
+                        // or (AD-PSGD) the live parameters, which may already carry
+                        // newer local SGD updates
+                        const float* own = (flags & SGP_F_SELF_FROM_Z) ? a.z : my_out;
+                        acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(own + i), pol_first),
+                                      (flags & SGP_F_SELF_FROM_Z) ? row.self_w * w0 : row.self_w);
                     }
-                    const float wk = row.in_w[k];
+                    // peer loads: all UNROLL requests of one peer in flight together
+                    for (int k = 0; k < row.n_in; ++k) {
+                        const float* po = peer_out[k];
+                        if (po == nullptr) continue;
 #pragma unroll
-                    for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(pv[u], wk, acc[u]);
-                }
+                        for (int u = 0; u < SGP_UNROLL; ++u) {
+                            const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                            pv[u] = ld_stream_f4(reinterpret_cast<const float4*>(po + i));
+                        }
+                        const float wk = row.in_w[k];
 #pragma unroll
-                for (int u = 0; u < SGP_UNROLL; ++u) {
-                    const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                    const float4 zv = mul4(acc[u], inv_wn);
-                    st_f4(reinterpret_cast<float4*>(a.z + i), zv);
-                    if (flags & SGP_F_SHADOW)
-                        st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                        for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(pv[u], wk, acc[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        const float4 zv = mul4(acc[u], inv_wn);
+                        st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                        if (flags & SGP_F_SHADOW)
+                            st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    }
                 }
             }
+            __syncthreads();     // s_ok / s_wn are rewritten by the next segment
         }
     }
 
@@ -298,6 +318,8 @@ sgp_gather_kernel(const SgpArgs a, const int pub_grid)
 
     RowInfo row;
     load_row(a, s, row);
+    int segs = a.segments < 1 ? 1 : a.segments;
+    if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
 
     // every CTA waits for ALL publisher CTAs of every in-neighbour (block-parallel poll)
     if (tid == 0) s_ok = 1;
@@ -307,7 +329,8 @@ sgp_gather_kernel(const SgpArgs a, const int pub_grid)
         if (j < 0) continue;
         const SgpSignalPad* pj = a.pads[j];
         for (int f = tid; f < pub_grid; f += SGP_THREADS)
-            if (!spin_wait_geq(&pj->pub_seq[f], s + 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_PUB))
+            if (!spin_wait_geq(&pj->pub_seq[f], s * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs, st,
+                               a.timeout_ns, SGP_ERR_TIMEOUT_PUB))
                 s_ok = 0;
     }
     __syncthreads();
@@ -365,13 +388,16 @@ __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* 
     const uint32_t step = *((volatile uint32_t*)&st->step);
     RowInfo row;
     load_row(a, step, row);
+    int segs = a.segments < 1 ? 1 : a.segments;
+    if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
     if (threadIdx.x == 0) s_all = 1;
     __syncthreads();
     for (int k = 0; k < row.n_in; ++k) {
         const int j = row.in[k];
         if (j < 0) continue;
         for (int f = threadIdx.x; f < pub_grid; f += blockDim.x)
-            if ((int32_t)(ld_acquire_sys(&a.pads[j]->pub_seq[f]) - (step + 1u)) < 0) s_all = 0;
+            if ((int32_t)(ld_acquire_sys(&a.pads[j]->pub_seq[f]) -
+                          (step * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs)) < 0) s_all = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

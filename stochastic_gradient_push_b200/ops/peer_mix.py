@@ -65,7 +65,7 @@ class GossipEngine(object):
                  shadow: Optional[torch.Tensor] = None,
                  with_residual: bool = False,
                  grid: Optional[int] = None, gather_grid: Optional[int] = None,
-                 timeout_s: float = 30.0, name: str = 'sgp'):
+                 timeout_s: float = 30.0, name: str = 'sgp', segments: int = 4):
         C = native.load()
         self.C = C
         self.world = world
@@ -105,6 +105,8 @@ class GossipEngine(object):
             table=table, wtable=wtable, rank=self.rank, world=self.nranks,
             state=self.state, hyper=self.hyper, timeout_s=float(timeout_s))
         self.period = table.shape[0]
+        # phase-1 / phase-2 interleave granularity; must be identical on all ranks
+        self.ctx.set_segments(int(segments))
         self.max_grid = self.ctx.max_grid()
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         nchunks = self.n // C.CHUNK
