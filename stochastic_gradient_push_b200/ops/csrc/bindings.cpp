@@ -207,13 +207,16 @@ public:
         SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
     }
 
-    void gather(int grid, int pub_grid)
+    void gather(int grid, int pub_grid, bool tma)
     {
         check_grid(grid);
         SgpArgs a = prepare(0);
         TORCH_CHECK(a.residual && a.outboxes);
         c10::cuda::CUDAGuard guard(device_);
-        SGP_CUDA_CHECK(sgp_launch_gather(&a, grid, pub_grid, at::cuda::getCurrentCUDAStream()));
+        if (tma)
+            SGP_CUDA_CHECK(sgp_launch_gather_tma(&a, grid, pub_grid, at::cuda::getCurrentCUDAStream()));
+        else
+            SGP_CUDA_CHECK(sgp_launch_gather(&a, grid, pub_grid, at::cuda::getCurrentCUDAStream()));
     }
 
     void probe(int pub_grid, c10::optional<torch::Tensor> host_flag)
@@ -362,7 +365,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("segments", &GossipContext::segments)
         .def("max_grid", &GossipContext::max_grid)
         .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))
-        .def("gather", &GossipContext::gather, py::arg("grid"), py::arg("pub_grid"))
+        .def("gather", &GossipContext::gather, py::arg("grid"), py::arg("pub_grid"), py::arg("tma") = false)
         .def("probe", &GossipContext::probe, py::arg("pub_grid"), py::arg("host_flag") = py::none())
         .def("allreduce_sgd", &GossipContext::allreduce_sgd)
         .def("barrier", &GossipContext::barrier);

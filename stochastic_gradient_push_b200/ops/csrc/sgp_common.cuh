@@ -233,6 +233,7 @@ __device__ __forceinline__ bool spin_wait_geq(const uint32_t* flag, uint32_t wan
 extern "C" {
 cudaError_t sgp_launch_step(const SgpArgs* args, int grid, cudaStream_t stream);
 cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
+cudaError_t sgp_launch_gather_tma(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
 cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_flag,
                              cudaStream_t stream);
 cudaError_t sgp_launch_zero(void* p, long long bytes, cudaStream_t stream);

@@ -379,6 +379,139 @@ sgp_gather_kernel(const SgpArgs a, const int pub_grid)
 }
 
 // ---------------------------------------------------------------------------
+// Overlap-SGP gather, TMA variant.  The gather runs on a side stream next to the
+// forward/backward pass, so it should saturate NVLink from as FEW SMs as possible.
+// Register-staged loads need ~300 CTAs of in-flight 16-byte requests to cover the
+// ~2 us NVLink latency; here one elected thread per CTA keeps a ring of
+// SGP_TMA_STAGES x 16 KB bulk copies (cp.async.bulk, global[peer] -> shared,
+// mbarrier complete_tx) in flight, i.e. ~100 KB per CTA instead of ~16 KB, and the
+// whole CTA only touches the data once it has landed in shared memory.
+// ---------------------------------------------------------------------------
+#define SGP_TMA_STAGES 6
+#define SGP_TMA_BYTES  (SGP_CHUNK * 4)      // one 4096-float chunk = 16 KB per stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SGP_THREADS, 1)
+sgp_gather_tma_kernel(const SgpArgs a, const int pub_grid)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                       // [STAGES][CHUNK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + SGP_TMA_STAGES * SGP_TMA_BYTES);
+    __shared__ int s_ok;
+
+    SgpState* st = a.st;
+    const uint32_t s      = *((volatile uint32_t*)&st->step) - 1u;
+    const uint32_t parity = s & 1u;
+    const int tid = threadIdx.x;
+    const long long nchunks = a.n / SGP_CHUNK;
+
+    RowInfo row;
+    load_row(a, s, row);
+    int segs = a.segments < 1 ? 1 : a.segments;
+    if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
+
+    if (tid == 0) {
+        s_ok = 1;
+        for (int i = 0; i < SGP_TMA_STAGES; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int k = 0; k < row.n_in; ++k) {
+        const int j = row.in[k];
+        if (j < 0) continue;
+        const SgpSignalPad* pj = a.pads[j];
+        for (int f = tid; f < pub_grid; f += SGP_THREADS)
+            if (!spin_wait_geq(&pj->pub_seq[f], s * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs, st,
+                               a.timeout_ns, SGP_ERR_TIMEOUT_PUB))
+                s_ok = 0;
+    }
+    __syncthreads();
+
+    const int n_in = row.n_in;
+    const long long my_chunks = (nchunks > blockIdx.x) ? (nchunks - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long long items = s_ok ? my_chunks * n_in : 0;     // (chunk, in-peer) pairs, peer fastest
+
+    auto issue = [&](long long item) {
+        const long long it = item / n_in;
+        const int k = (int)(item - it * n_in);
+        const long long c = blockIdx.x + it * gridDim.x;
+        const int stage = (int)(item % SGP_TMA_STAGES);
+        const float* src = a.outboxes[row.in[k]] + (size_t)parity * a.n + c * SGP_CHUNK;
+        mbar_expect_tx(&full[stage], SGP_TMA_BYTES);
+        tma_load_1d(ring + (size_t)stage * SGP_CHUNK, src, SGP_TMA_BYTES, &full[stage]);
+    };
+
+    if (tid == 0)
+        for (long long i = 0; i < items && i < SGP_TMA_STAGES; ++i) issue(i);
+
+    float4 acc[SGP_UNROLL];
+    for (long long item = 0; item < items; ++item) {
+        const long long it = item / n_in;
+        const int k = (int)(item - it * n_in);
+        const int stage = (int)(item % SGP_TMA_STAGES);
+        mbar_wait(&full[stage], (uint32_t)((item / SGP_TMA_STAGES) & 1));
+        const float4* src = reinterpret_cast<const float4*>(ring + (size_t)stage * SGP_CHUNK);
+        const float wk = row.in_w[k];
+#pragma unroll
+        for (int u = 0; u < SGP_UNROLL; ++u) {
+            const float4 v = src[tid + u * SGP_THREADS];
+            acc[u] = (k == 0) ? mul4(v, wk) : fma4(v, wk, acc[u]);
+        }
+        if (k == n_in - 1) {
+            const long long c = blockIdx.x + it * gridDim.x;
+            float4* dst = reinterpret_cast<float4*>(a.residual + c * SGP_CHUNK);
+#pragma unroll
+            for (int u = 0; u < SGP_UNROLL; ++u) st_f4(dst + tid + u * SGP_THREADS, acc[u]);
+        }
+        __syncthreads();                         // every thread is done with this stage
+        if (tid == 0 && item + SGP_TMA_STAGES < items) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async write
+            issue(item + SGP_TMA_STAGES);
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0 && cta_done_is_last(st)) {
+        float wr = 0.f;
+        for (int k = 0; k < row.n_in; ++k) {
+            const int j = row.in[k];
+            if (j < 0) continue;
+            wr = fmaf(row.in_w[k], ld_relaxed_sys_f32(&a.pads[j]->psw[parity]), wr);
+            if (j != a.rank) st_release_sys(&a.pads[j]->ack_seq[a.rank], s + 1u);
+        }
+        *((volatile float*)&st->res_weight) = s_ok ? wr : 0.f;
+        *((volatile uint32_t*)&st->done_ctas) = 0u;
+        __threadfence();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // AD-PSGD passive poll: did the in-neighbour of the current round publish?
 // ---------------------------------------------------------------------------
 __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* host_flag)
@@ -574,6 +707,20 @@ cudaError_t sgp_launch_step(const SgpArgs* args, int grid, cudaStream_t stream)
 cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream)
 {
     sgp_gather_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args, pub_grid);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_gather_tma(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream)
+{
+    const int smem = SGP_TMA_STAGES * SGP_TMA_BYTES + SGP_TMA_STAGES * 8 + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sgp_gather_tma_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sgp_gather_tma_kernel<<<grid, SGP_THREADS, smem, stream>>>(*args, pub_grid);
     return cudaGetLastError();
 }
 

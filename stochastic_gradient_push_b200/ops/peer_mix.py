@@ -65,7 +65,8 @@ class GossipEngine(object):
                  shadow: Optional[torch.Tensor] = None,
                  with_residual: bool = False,
                  grid: Optional[int] = None, gather_grid: Optional[int] = None,
-                 timeout_s: float = 30.0, name: str = 'sgp', segments: int = 4):
+                 timeout_s: float = 30.0, name: str = 'sgp', segments: int = 4,
+                 gather_tma: bool = True):
         C = native.load()
         self.C = C
         self.world = world
@@ -117,6 +118,7 @@ class GossipEngine(object):
         if gather_grid is None:
             gather_grid = min(32, self.grid)
         self.gather_grid = int(max(1, min(gather_grid, nchunks)))
+        self.gather_tma = bool(gather_tma)
         self.steps = 0               # host mirror of SgpState.step
         self._graph_synced = 0       # rotations applied to the python graph object
         self.set_hyper(0.0, 0.0, 0.0, False, do_sgd=False)
@@ -186,8 +188,10 @@ class GossipEngine(object):
         self.ctx.step(f, self.grid)
         self.steps += 1
 
-    def gather(self):
-        self.ctx.gather(self.gather_grid, self.grid)
+    def gather(self, tma=None):
+        """residual <- sum_k in_w[k] * outbox_k (Overlap-SGP side stream); TMA bulk
+        copies by default, register-staged loads with ``tma=False``."""
+        self.ctx.gather(self.gather_grid, self.grid, self.gather_tma if tma is None else bool(tma))
 
     def local(self, sgd=False, fold=False, zero_grad=True, in_numerator=False):
         C = self.C
