@@ -24,7 +24,7 @@ def main():
     ap.add_argument('--numel', type=int, default=25559040 // 4096 * 4096 + 4096)
     ap.add_argument('--iters', type=int, default=6)
     ap.add_argument('--bf16', action='store_true')
-    ap.add_argument('--mode', default='mix', choices=['mix', 'local'])
+    ap.add_argument('--mode', default='mix', choices=['mix', 'local', 'gather'])
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     n = args.numel
@@ -35,9 +35,10 @@ def main():
         grad = grad.bfloat16()
     shadow = torch.zeros(n, device=dev, dtype=torch.bfloat16) if args.bf16 else None
     eng = GossipEngine(LocalWorld(1).view(0), z, graph, sgp.UniformMixing(graph, dev), grad=grad,
-                       momentum=torch.zeros(n, device=dev), shadow=shadow, timeout_s=5.0)
+                       momentum=torch.zeros(n, device=dev), shadow=shadow, timeout_s=5.0,
+                       with_residual=True, gather_grid=32)
     C = eng.C
-    if args.mode == 'mix':
+    if args.mode in ('mix', 'gather'):
         table = torch.full((1, C.TABLE_ROW), -1, dtype=torch.int32, device=dev)
         table[0, 0] = 1      # n_in
         table[0, 1] = 1      # n_out
@@ -53,6 +54,10 @@ def main():
         flush.zero_()
         if args.mode == 'mix':
             eng.mix(sgd=True, zero_grad=True)
+        elif args.mode == 'gather':
+            eng.publish(sgd=False)
+            flush.zero_()
+            eng.gather()
         else:
             eng.local(sgd=True, zero_grad=True)
         torch.cuda.synchronize()

@@ -13,6 +13,7 @@ namespace py = pybind11;
 extern "C" {
 int bn_supported(long long M, int C);
 int bn_partial_rows(long long M, int C);
+int bn_partial_rows_bwd(long long M, int C);
 cudaError_t bn_launch_stats(int dtype, const void* x, float* partial, long long M, int C, int G, cudaStream_t st);
 cudaError_t bn_launch_stats_finalize(const float* partial, int G, long long M, int C, const float* gamma,
                                      const float* beta, float* rmean, float* rvar, long long* nbt,
@@ -140,7 +141,7 @@ static std::vector<torch::Tensor> bn_backward(torch::Tensor dy, torch::Tensor x,
     const int mode = add ? 2 : (relu ? 1 : 0);
     TORCH_CHECK(!add || relu, "residual add without ReLU is plain autograd (not fused)");
     if (mode == 2) TORCH_CHECK(y.has_value() && y->defined() && y->strides() == x.strides());
-    const int G = bn_partial_rows(M, C);
+    const int G = bn_partial_rows_bwd(M, C);
     auto partial = torch::empty({G, 2, C}, fopt);
     auto grads = torch::empty({4, C}, fopt);    // grad_gamma, grad_beta, c2, c3
     float* gg = grads.data_ptr<float>();
