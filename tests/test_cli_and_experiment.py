@@ -184,3 +184,26 @@ def test_adpsgd_cli_two_ranks_cpu(tmp_path, master_port):
     assert out.returncode == 0, out.stdout[-3000:]
     size = os.stat(str(tmp_path / 'global_itr.txt')).st_size
     assert size >= 2 * 2 * 8        # >= num_epochs * world * itr_per_epoch bytes appended
+
+
+def _signal_worker(rank, world, ckpt_dir):
+    import torch.distributed as dist
+    ClusterManager.set_checkpoint_dir(ckpt_dir)
+    state = {'epoch': 1, 'is_best': False}
+    cm = ClusterManager(rank=rank, world_size=world, state=state, model_tag='sig_', all_workers=True)
+    cm.save_checkpoint(requeue_on_signal=True)           # nobody signalled: returns
+    if rank == 1:
+        os.kill(os.getpid(), signal.SIGUSR1)             # pre-emption notice on ONE rank
+    exited = False
+    try:
+        cm.save_checkpoint(requeue_on_signal=True)       # all ranks agree and exit(0)
+    except SystemExit as e:
+        exited = (e.code == 0)
+    return exited, os.path.isfile(cm.checkpoint_fpath)
+
+
+def test_cluster_manager_agrees_on_preemption_across_ranks(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from dist_utils import run_distributed
+    out = run_distributed(_signal_worker, 2, str(tmp_path) + '/')
+    assert out == [(True, True), (True, True)]

@@ -28,7 +28,8 @@ def _flat(model):
     return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
 
 
-def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, nesterov):
+def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, nesterov,
+            ppi_switch=None):
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
     from stochastic_gradient_push_b200.optim import FusedGossipSGD
     graph = getattr(sgp, graph_name)(rank, world, peers_per_itr=ppi)
@@ -42,6 +43,8 @@ def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, neste
                               nesterov=nesterov)
     model.train()
     for step in range(steps):
+        if ppi_switch is not None and step == ppi_switch[0]:
+            model.update_gossiper('peers_per_itr', ppi_switch[1])
         x, y = _batch(rank, step)
         loss = ((model(x) - y) ** 2).mean()
         loss.backward()
@@ -55,7 +58,7 @@ def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, neste
     return _flat(model.module).tolist(), float(sd['ps_weight']), sd['is_ps_numerator']
 
 
-def _simulate(world, graph_name, ppi, steps, overlap, nesterov):
+def _simulate(world, graph_name, ppi, steps, overlap, nesterov, ppi_switch=None):
     """All ranks in one process, plain tensors, straight from the algebra in
     SURVEY 3.3/3.4."""
     models = [_model(r) for r in range(world)]
@@ -75,6 +78,14 @@ def _simulate(world, graph_name, ppi, steps, overlap, nesterov):
             off += n
 
     for step in range(steps):
+        if ppi_switch is not None and step == ppi_switch[0]:
+            if overlap:          # a schedule change drains the in-flight gossip first
+                xs = [x + r for x, r in zip(xs, res)]
+                ws = [w + wr for w, wr in zip(ws, wres)]
+                res = [torch.zeros_like(x) for x in xs]
+                wres = [0.0] * world
+            for g in graphs:
+                g.peers_per_itr = ppi_switch[1]
         if overlap:
             # pre-forward: fold residual, pre-scale, snapshot & send
             xs = [x + r for x, r in zip(xs, res)]
@@ -248,3 +259,15 @@ def test_hierarchical_nprocs_per_node():
     torch.testing.assert_close(p[2], p[3], rtol=0, atol=0)
     # two nodes on a 1-peer graph average exactly at every mix
     torch.testing.assert_close(p[0], p[2], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('overlap', [False, True])
+def test_peers_per_itr_switch_mid_training_matches_simulation(overlap):
+    world, steps, switch = 4, 6, (3, 2)
+    name = 'DynamicDirectedExponentialGraph'
+    out = run_distributed(_worker, world, name, 1, steps, True, overlap, True, False, switch)
+    want, ws = _simulate(world, name, 1, steps, overlap, False, switch)
+    for r in range(world):
+        got, w, _ = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5

@@ -104,7 +104,7 @@ def test_random_skew_conserves_mass():
 # --------------------------------------------------------------------------- #
 # GossipDataParallel on the nvlink kernel transport vs the world simulation
 # --------------------------------------------------------------------------- #
-def _gdp_worker(rank, world, graph_name, ppi, steps, overlap, fused, nesterov):
+def _gdp_worker(rank, world, graph_name, ppi, steps, overlap, fused, nesterov, ppi_switch=None):
     import test_distributed_c10d as sim
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
     from stochastic_gradient_push_b200.optim import FusedGossipSGD
@@ -122,6 +122,8 @@ def _gdp_worker(rank, world, graph_name, ppi, steps, overlap, fused, nesterov):
                               weight_decay=sim.WD, nesterov=nesterov)
     model.train()
     for step in range(steps):
+        if ppi_switch is not None and step == ppi_switch[0]:
+            model.update_gossiper('peers_per_itr', ppi_switch[1])
         x, y = sim._batch(rank, step)
         loss = ((model(x.to(dev)) - y.to(dev)) ** 2).mean()
         loss.backward()
@@ -319,3 +321,47 @@ def test_standalone_pushsum_on_peer_memory(residual):
         want = {0: [5, 5, 5], 1: [5, 5, 5]}
     for r in range(n):
         assert out[r] == want[r], out
+
+
+@pytest.mark.parametrize('overlap', [False, True])
+def test_device_schedule_swap_on_peers_per_itr_change(overlap):
+    """update_gossiper('peers_per_itr') re-emits the device tables mid-training
+    (phase_base / ack_from bookkeeping) -- must match the world simulation."""
+    import test_distributed_c10d as sim
+    n = 4 if _ngpu() >= 4 else 2
+    steps, switch, name = 6, (3, 2), 'DynamicDirectedExponentialGraph'
+    out = run_distributed(_gdp_worker, n, name, 1, steps, overlap, True, False, switch,
+                          backend='nccl', timeout=300)
+    want, ws = sim._simulate(n, name, 1, steps, overlap, False, switch)
+    for r in range(n):
+        got, w = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5
+
+
+def _async_gpu_worker(rank, world, synch_freq, steps):
+    import test_distributed_c10d as sim
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    dev = torch.device('cuda', rank)
+    graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world)
+    model = GossipDataParallel(sim._model(rank).to(dev), graph=graph, overlap=True,
+                               synch_freq=synch_freq, rank=rank, world_size=world,
+                               heartbeat_timeout=30)
+    x = torch.zeros(2, 6, device=dev)
+    for _ in range(steps):
+        model(x)
+    model.sync_comms()
+    model.unbias()
+    torch.cuda.synchronize()
+    model.engine.check()
+    return sim._flat(model.module).cpu().tolist(), float(model.ps_weight)
+
+
+def test_bounded_staleness_on_kernels_conserves_mass():
+    import test_distributed_c10d as sim
+    n = 4 if _ngpu() >= 4 else 2
+    out = run_distributed(_async_gpu_worker, n, 2, 12, backend='nccl', timeout=300)
+    x0 = torch.stack([sim._flat(sim._model(r)) for r in range(n)])
+    mass = sum(torch.tensor(z) * w for z, w in out)
+    torch.testing.assert_close(mass, x0.sum(0), rtol=1e-4, atol=1e-4)
+    assert abs(sum(w for _, w in out) - n) < 1e-4
