@@ -162,13 +162,12 @@ def run_ours(args):
                              weight_decay=1e-4, nesterov=True)
         trainer = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=not args.no_graph)
         kernels_per_step = 2 if (args.algo == 'osgp' and world > 1) else 1
-    # our own sm_100a kernels per training step: 4 per fused BatchNorm (stats+finalize,
-    # apply | reduce+finalize, dx; 6 without the fused finalisation), 2 per NHWC max-pool,
-    # plus the gossip kernel(s)
+    # our own sm_100a kernels per training step: 6 per fused BatchNorm (stats, finalize,
+    # apply | reduce, finalize, dx), 2 per NHWC max-pool, plus the gossip kernel(s)
     from stochastic_gradient_push_b200.ops.fused_bn import FusedBatchNormAct2d, MaxPool2dNHWC
     n_bn = sum(isinstance(m, FusedBatchNormAct2d) for m in net.modules())
     n_pool = sum(isinstance(m, MaxPool2dNHWC) for m in net.modules())
-    kernels_per_step += (4 if FusedBatchNormAct2d.fuse_finalize else 6) * n_bn + 2 * n_pool
+    kernels_per_step += 6 * n_bn + 2 * n_pool
 
     # synthetic data: a small pool of pinned host batches (the loader's output)
     g = torch.Generator().manual_seed(1234 + rank)

@@ -26,12 +26,7 @@ cudaError_t bn_launch_apply(int dtype, int relu, int add, const void* x, const v
 cudaError_t bn_launch_bwd_reduce(int dtype, int mode, const void* dy, const void* x, const void* y,
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, float* partial, void* dz, long long M, int C,
-                                 int G, float* ws, float* ggamma, float* gbeta, float* c2, float* c3,
-                                 cudaStream_t st);
-cudaError_t bn_launch_stats_fused(int dtype, const void* x, float* ws, long long M, int C, int G,
-                                  const float* gamma, const float* beta, float* rmean, float* rvar,
-                                  long long* nbt, float momentum, float eps, float* mean,
-                                  float* invstd, float* scale, float* shift, cudaStream_t st);
+                                 int G, cudaStream_t st);
 cudaError_t bn_launch_bwd_finalize(const float* partial, int G, long long M, int C, const float* scale,
                                    const float* mean, const float* invstd, float* ggamma, float* gbeta,
                                    float* c2, float* c3, cudaStream_t st);
@@ -84,8 +79,7 @@ static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torc
                                              c10::optional<torch::Tensor> running_mean,
                                              c10::optional<torch::Tensor> running_var,
                                              c10::optional<torch::Tensor> num_batches_tracked,
-                                             bool training, double momentum, double eps, bool relu,
-                                             c10::optional<torch::Tensor> workspace)
+                                             bool training, double momentum, double eps, bool relu)
 {
     long long M; int C;
     nhwc_dims(x, M, C);
@@ -104,6 +98,8 @@ static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torc
                              && residual->strides() == x.strides());
     if (training) {
         const int G = bn_partial_rows(M, C);
+        auto partial = torch::empty({G + 1, 2, C}, fopt);   // last row carries the shift K
+        BN_CHECK(bn_launch_stats(dt, x.data_ptr(), partial.data_ptr<float>(), M, C, G, st));
         float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
         if (running_mean.has_value() && running_mean->defined()) {
             rm = running_mean->data_ptr<float>();
@@ -111,18 +107,9 @@ static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torc
         }
         if (num_batches_tracked.has_value() && num_batches_tracked->defined())
             nbt = reinterpret_cast<long long*>(num_batches_tracked->data_ptr<int64_t>());
-        if (workspace.has_value() && workspace->defined()) {
-            TORCH_CHECK(workspace->scalar_type() == torch::kFloat32 && workspace->numel() >= 2 * C + 1);
-            BN_CHECK(bn_launch_stats_fused(dt, x.data_ptr(), workspace->data_ptr<float>(), M, C, G,
-                                           gamma.data_ptr<float>(), beta.data_ptr<float>(), rm, rv, nbt,
-                                           (float)momentum, (float)eps, mean, invstd, scale, shift, st));
-        } else {
-            auto partial = torch::empty({G + 1, 2, C}, fopt);   // last row carries the shift K
-            BN_CHECK(bn_launch_stats(dt, x.data_ptr(), partial.data_ptr<float>(), M, C, G, st));
-            BN_CHECK(bn_launch_stats_finalize(partial.data_ptr<float>(), G, M, C, gamma.data_ptr<float>(),
-                                              beta.data_ptr<float>(), rm, rv, nbt, (float)momentum,
-                                              (float)eps, mean, invstd, scale, shift, st));
-        }
+        BN_CHECK(bn_launch_stats_finalize(partial.data_ptr<float>(), G, M, C, gamma.data_ptr<float>(),
+                                          beta.data_ptr<float>(), rm, rv, nbt, (float)momentum,
+                                          (float)eps, mean, invstd, scale, shift, st));
     } else {
         TORCH_CHECK(running_mean.has_value() && running_var.has_value());
         BN_CHECK(bn_launch_eval_coeff(C, gamma.data_ptr<float>(), beta.data_ptr<float>(),
@@ -138,8 +125,7 @@ static std::vector<torch::Tensor> bn_forward(torch::Tensor x, c10::optional<torc
 // returns (dx, dres or undefined, grad_gamma, grad_beta)
 static std::vector<torch::Tensor> bn_backward(torch::Tensor dy, torch::Tensor x,
                                               c10::optional<torch::Tensor> y, torch::Tensor coef,
-                                              bool relu, bool add,
-                                              c10::optional<torch::Tensor> workspace)
+                                              bool relu, bool add)
 {
     long long M; int C;
     nhwc_dims(x, M, C);
@@ -156,25 +142,17 @@ static std::vector<torch::Tensor> bn_backward(torch::Tensor dy, torch::Tensor x,
     TORCH_CHECK(!add || relu, "residual add without ReLU is plain autograd (not fused)");
     if (mode == 2) TORCH_CHECK(y.has_value() && y->defined() && y->strides() == x.strides());
     const int G = bn_partial_rows_bwd(M, C);
+    auto partial = torch::empty({G, 2, C}, fopt);
     auto grads = torch::empty({4, C}, fopt);    // grad_gamma, grad_beta, c2, c3
     float* gg = grads.data_ptr<float>();
     torch::Tensor dz;
     if (mode == 2) dz = torch::empty_like(x);
-    if (workspace.has_value() && workspace->defined()) {
-        TORCH_CHECK(workspace->scalar_type() == torch::kFloat32 && workspace->numel() >= 2 * C + 1);
-        BN_CHECK(bn_launch_bwd_reduce(dt, mode, dy.data_ptr(), x.data_ptr(),
-                                      mode == 2 ? y->data_ptr() : nullptr, scale, shift, mean, invstd,
-                                      nullptr, mode == 2 ? dz.data_ptr() : nullptr, M, C, G,
-                                      workspace->data_ptr<float>(), gg, gg + C, gg + 2 * C, gg + 3 * C, st));
-    } else {
-        auto partial = torch::empty({G, 2, C}, fopt);
-        BN_CHECK(bn_launch_bwd_reduce(dt, mode, dy.data_ptr(), x.data_ptr(),
-                                      mode == 2 ? y->data_ptr() : nullptr, scale, shift, mean, invstd,
-                                      partial.data_ptr<float>(), mode == 2 ? dz.data_ptr() : nullptr,
-                                      M, C, G, nullptr, gg, gg + C, gg + 2 * C, gg + 3 * C, st));
-        BN_CHECK(bn_launch_bwd_finalize(partial.data_ptr<float>(), G, M, C, scale, mean, invstd,
-                                        gg, gg + C, gg + 2 * C, gg + 3 * C, st));
-    }
+    BN_CHECK(bn_launch_bwd_reduce(dt, mode, dy.data_ptr(), x.data_ptr(),
+                                  mode == 2 ? y->data_ptr() : nullptr, scale, shift, mean, invstd,
+                                  partial.data_ptr<float>(), mode == 2 ? dz.data_ptr() : nullptr,
+                                  M, C, G, st));
+    BN_CHECK(bn_launch_bwd_finalize(partial.data_ptr<float>(), G, M, C, scale, mean, invstd,
+                                    gg, gg + C, gg + 2 * C, gg + 3 * C, st));
     auto dx = torch::empty_like(x);
     BN_CHECK(bn_launch_bwd_dx(dt, mode == 1 ? 1 : 0, mode == 2 ? dz.data_ptr() : dy.data_ptr(),
                               x.data_ptr(), scale, shift, gg + 2 * C, gg + 3 * C, dx.data_ptr(),

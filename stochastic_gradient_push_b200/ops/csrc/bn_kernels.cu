@@ -43,17 +43,18 @@ struct Map {
     }
 };
 
-// block reduce of 2 x 8 per-thread accumulators across the row lanes that share a
-// channel vector; afterwards threads [0, tpr) hold the CTA totals of "their" 8 channels
-__device__ __forceinline__ bool block_reduce16(const Map& mp, const F8& a, const F8& b, float (&acc)[16])
+// block reduce of 2 x 8 per-thread accumulators across the row lanes that share
+// a channel vector, then one partial row per CTA: partial[blockIdx][2][C]
+__device__ __forceinline__ void reduce_store_partials(const Map& mp, const F8& a, const F8& b,
+                                                      float* __restrict__ partial, int C)
 {
     __shared__ float sm[BN_THREADS * 16];
     float* mine = sm + threadIdx.x * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mine[i] = mp.active ? a.v[i] : 0.f; mine[8 + i] = mp.active ? b.v[i] : 0.f; }
     __syncthreads();
-    const bool owner = threadIdx.x < mp.tpr;
-    if (owner) {
+    if (threadIdx.x < mp.tpr) {
+        float acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;
         for (int r = 0; r < mp.rpi; ++r) {
@@ -61,114 +62,20 @@ __device__ __forceinline__ bool block_reduce16(const Map& mp, const F8& a, const
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] += o[i];
         }
-    }
-    return owner;
-}
-
-// Two ways to combine the per-CTA totals:
-//  (a) deterministic: one partial row per CTA, partial[blockIdx][2][C], summed by a
-//      separate finalize kernel;
-//  (b) fused: fp32 atomics into a per-module, self-cleaning workspace
-//      ws = [sum_a[C] | sum_b[C] | ticket]; the LAST CTA to arrive runs the per-channel
-//      finalisation itself -- no finalize launch (158 launches, ~1 ms per ResNet-50
-//      step).  Returns true (block-uniform) in that last CTA.
-__device__ __forceinline__ bool combine_partials(const Map& mp, const F8& a, const F8& b,
-                                                 float* __restrict__ partial,
-                                                 float* __restrict__ ws, int C)
-{
-    __shared__ int s_last;
-    float acc[16];
-    const bool owner = block_reduce16(mp, a, b, acc);
-    if (ws == nullptr) {
-        if (owner) {
-            float* out = partial + (size_t)blockIdx.x * 2 * C + threadIdx.x * BN_VEC;
+        float* out = partial + (size_t)blockIdx.x * 2 * C + threadIdx.x * BN_VEC;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { out[i] = acc[i]; out[C + i] = acc[8 + i]; }
-        }
-        return false;
+        for (int i = 0; i < 8; ++i) { out[i] = acc[i]; out[C + i] = acc[8 + i]; }
     }
-    if (owner) {
-        float* out = ws + threadIdx.x * BN_VEC;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { atomicAdd(out + i, acc[i]); atomicAdd(out + C + i, acc[8 + i]); }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(ws + 2 * C), 1u);
-        s_last = (ticket == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last != 0;
-}
-
-__device__ __forceinline__ float ws_take(float* p) {      // read-and-clear (self-cleaning)
-    const float v = *((volatile float*)p);
-    *((volatile float*)p) = 0.f;
-    return v;
 }
 
 }  // namespace
-
-template <typename T> __device__ __forceinline__ float elem_as_float(const T* p);
-template <> __device__ __forceinline__ float elem_as_float<float>(const float* p) { return *p; }
-template <> __device__ __forceinline__ float elem_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
-    return __bfloat162float(*p);
-}
-
-struct BnFwdFin {            // everything the forward finalisation needs
-    const float* gamma; const float* beta;
-    float* running_mean; float* running_var; long long* nbt;
-    float momentum, eps;
-    float* mean; float* invstd; float* scale; float* shift;
-};
-
-__device__ __forceinline__ void bn_fwd_finalize_channel(const BnFwdFin& f, int c, float s, float q,
-                                                        float k, long long M)
-{
-    const float inv_m = 1.f / (float)M;
-    const float ds = s * inv_m;
-    const float mu = k + ds;
-    const float var = fmaxf(fmaf(-ds, ds, q * inv_m), 0.f);
-    const float is = rsqrtf(var + f.eps);
-    f.mean[c] = mu;
-    f.invstd[c] = is;
-    const float sc = f.gamma[c] * is;
-    f.scale[c] = sc;
-    f.shift[c] = fmaf(-mu, sc, f.beta[c]);
-    if (f.running_mean != nullptr) {
-        const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
-        f.running_mean[c] = fmaf(f.momentum, mu - f.running_mean[c], f.running_mean[c]);
-        f.running_var[c] = fmaf(f.momentum, unbiased - f.running_var[c], f.running_var[c]);
-    }
-}
-
-struct BnBwdFin {
-    const float* scale; const float* mean; const float* invstd;
-    float* grad_gamma; float* grad_beta; float* c2; float* c3;
-};
-
-__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFin& f, int c, float s, float q,
-                                                        long long M)
-{
-    f.grad_beta[c] = s;
-    f.grad_gamma[c] = q;
-    const float inv_m = 1.f / (float)M;
-    const float k1 = s * inv_m, k2 = q * inv_m;
-    const float a = f.invstd[c] * k2;          // xhat*k2 = x*a - mean*a
-    const float sc = f.scale[c];
-    f.c2[c] = sc * a;
-    f.c3[c] = sc * (f.mean[c] * a - k1);
-}
 
 // ---------------------------------------------------------------------------
 // forward: statistics
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 4)
-bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long M, int C,
-                float* __restrict__ ws, const BnFwdFin fin)
+bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long M, int C)
 {
     const Map mp(C);
     F8 s, q;
@@ -181,7 +88,7 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
         // shifted sums: accumulate (x - K) with K = x[row 0] so that
         // var = E[(x-K)^2] - E[x-K]^2 does not cancel when |mean| >> std
         const F8 k = Io<T>::load(base);
-        if (ws == nullptr && blockIdx.x == 0 && mp.rl == 0) {
+        if (blockIdx.x == 0 && mp.rl == 0) {
             float* krow = partial + (size_t)gridDim.x * 2 * C + mp.cv * BN_VEC;
 #pragma unroll
             for (int i = 0; i < 8; ++i) krow[i] = k.v[i];
@@ -209,15 +116,7 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
             }
         }
     }
-    if (combine_partials(mp, s, q, partial, ws, C)) {
-        if (threadIdx.x == 0) {
-            *reinterpret_cast<unsigned int*>(ws + 2 * C) = 0u;
-            if (fin.nbt != nullptr) *fin.nbt += 1;
-        }
-        for (int c = threadIdx.x; c < C; c += BN_THREADS)
-            bn_fwd_finalize_channel(fin, c, ws_take(ws + c), ws_take(ws + C + c),
-                                    elem_as_float<T>(x + c), M);
-    }
+    reduce_store_partials(mp, s, q, partial, C);
 }
 
 // Finalize kernels: a CTA owns 32 channels; its 1024 threads are 32 partial-row
@@ -360,8 +259,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                     float* __restrict__ partial, T* __restrict__ dz_out, long long M, int C,
-                     float* __restrict__ ws, const BnBwdFin fin)
+                     float* __restrict__ partial, T* __restrict__ dz_out, long long M, int C)
 {
     const Map mp(C);
     F8 s, q;
@@ -408,11 +306,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
             }
         }
     }
-    if (combine_partials(mp, s, q, partial, ws, C)) {
-        if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + 2 * C) = 0u;
-        for (int c = threadIdx.x; c < C; c += BN_THREADS)
-            bn_bwd_finalize_channel(fin, c, ws_take(ws + c), ws_take(ws + C + c), M);
-    }
+    reduce_store_partials(mp, s, q, partial, C);
 }
 
 // per-channel: grad_gamma, grad_beta and the dx coefficients
@@ -511,21 +405,8 @@ int bn_partial_rows_bwd(long long M, int C) { return bn_grid(M, C, 3); }
 cudaError_t bn_launch_stats(int dtype, const void* x, float* partial, long long M, int C, int G,
                             cudaStream_t st)
 {
-    BnFwdFin none = {};
-    if (dtype == 0) bn_stats_kernel<__nv_bfloat16><<<G, BN_THREADS, 0, st>>>((const __nv_bfloat16*)x, partial, M, C, nullptr, none);
-    else            bn_stats_kernel<float><<<G, BN_THREADS, 0, st>>>((const float*)x, partial, M, C, nullptr, none);
-    return cudaGetLastError();
-}
-
-// statistics + finalisation in ONE launch (workspace = 2*C+1 floats, zero, self-cleaning)
-cudaError_t bn_launch_stats_fused(int dtype, const void* x, float* ws, long long M, int C, int G,
-                                  const float* gamma, const float* beta, float* rmean, float* rvar,
-                                  long long* nbt, float momentum, float eps, float* mean,
-                                  float* invstd, float* scale, float* shift, cudaStream_t st)
-{
-    BnFwdFin fin = {gamma, beta, rmean, rvar, nbt, momentum, eps, mean, invstd, scale, shift};
-    if (dtype == 0) bn_stats_kernel<__nv_bfloat16><<<G, BN_THREADS, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, ws, fin);
-    else            bn_stats_kernel<float><<<G, BN_THREADS, 0, st>>>((const float*)x, nullptr, M, C, ws, fin);
+    if (dtype == 0) bn_stats_kernel<__nv_bfloat16><<<G, BN_THREADS, 0, st>>>((const __nv_bfloat16*)x, partial, M, C);
+    else            bn_stats_kernel<float><<<G, BN_THREADS, 0, st>>>((const float*)x, partial, M, C);
     return cudaGetLastError();
 }
 
@@ -569,16 +450,13 @@ cudaError_t bn_launch_apply(int dtype, int relu, int add, const void* x, const v
 }
 
 #define BN_RED(T, MODE) bn_bwd_reduce_kernel<T, MODE><<<G, BN_THREADS, 0, st>>>( \
-    (const T*)dy, (const T*)x, (const T*)y, scale, shift, mean, invstd, partial, (T*)dz, M, C, ws, fin)
+    (const T*)dy, (const T*)x, (const T*)y, scale, shift, mean, invstd, partial, (T*)dz, M, C)
 
 cudaError_t bn_launch_bwd_reduce(int dtype, int mode, const void* dy, const void* x, const void* y,
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, float* partial, void* dz, long long M, int C,
-                                 int G, float* ws, float* ggamma, float* gbeta, float* c2, float* c3,
-                                 cudaStream_t st)
+                                 int G, cudaStream_t st)
 {
-    // ws != nullptr: accumulate with atomics and finalise in the last CTA (one launch)
-    BnBwdFin fin = {scale, mean, invstd, ggamma, gbeta, c2, c3};
     if (dtype == 0) {
         if (mode == 0) BN_RED(__nv_bfloat16, 0); else if (mode == 1) BN_RED(__nv_bfloat16, 1); else BN_RED(__nv_bfloat16, 2);
     } else {

@@ -40,11 +40,10 @@ class _FusedBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt,
-                training, momentum, eps, relu, ws_fwd, ws_bwd):
+                training, momentum, eps, relu):
         C = native.load()
         y, coef = C.bn_forward(x, residual, weight, bias, running_mean, running_var, nbt,
-                               training, momentum, eps, relu, ws_fwd)
-        ctx.ws_bwd = ws_bwd
+                               training, momentum, eps, relu)
         ctx.relu = relu
         ctx.add = residual is not None
         ctx.training = training
@@ -70,28 +69,20 @@ class _FusedBNAct(torch.autograd.Function):
                 out = y if ctx.add else torch.relu(F.batch_norm(x, None, None, training=False))
                 dz = dy * (out > 0)
             return dz * scale, (dz if ctx.add else None), None, None, None, None, None, \
-                None, None, None, None, None, None
-        dx, dz, ggamma, gbeta = C.bn_backward(dy, x, y, coef, ctx.relu, ctx.add, ctx.ws_bwd)
-        return dx, (dz if ctx.add else None), ggamma, gbeta, None, None, None, None, None, None, \
-            None, None, None
+                None, None, None, None
+        dx, dz, ggamma, gbeta = C.bn_backward(dy, x, y, coef, ctx.relu, ctx.add)
+        return dx, (dz if ctx.add else None), ggamma, gbeta, None, None, None, None, None, None, None
 
 
 def fused_bn_act(x, weight, bias, running_mean, running_var, num_batches_tracked=None,
-                 residual=None, relu=False, training=True, momentum=0.1, eps=1e-5,
-                 workspace=None):
-    """Functional form; falls back to plain PyTorch when the kernels cannot run.
-    ``workspace``: optional ``(fwd, bwd)`` pair of zero-initialised fp32 tensors of
-    ``2*C+1`` elements owned by the caller (self-cleaning): statistics are then
-    accumulated with atomics and finalised by the last CTA of the SAME launch
-    (4 launches per BN layer and step instead of 6; summation order -- and so the
-    last bits of the statistics -- is no longer run-to-run deterministic)."""
+                 residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+    """Functional form; falls back to plain PyTorch when the kernels cannot run."""
     fusable = _can_fuse(x) and weight is not None and weight.dtype == torch.float32 \
         and (residual is None or (relu and residual.dtype == x.dtype
                                   and residual.stride() == x.stride()))
     if fusable and (training or not torch.is_grad_enabled() or not x.requires_grad):
-        ws_f, ws_b = workspace if workspace is not None else (None, None)
         return _FusedBNAct.apply(x, residual, weight, bias, running_mean, running_var,
-                                 num_batches_tracked, training, momentum, eps, relu, ws_f, ws_b)
+                                 num_batches_tracked, training, momentum, eps, relu)
     return reference_bn_act(x, weight, bias, running_mean, running_var, num_batches_tracked,
                             residual, relu, training, momentum, eps)
 
@@ -109,19 +100,6 @@ def reference_bn_act(x, weight, bias, running_mean, running_var, num_batches_tra
 class FusedBatchNormAct2d(nn.BatchNorm2d):
     """``y = relu?(bn(x) (+ residual)?)`` -- see module docstring."""
 
-    fuse_finalize = True      # class-wide switch: atomics + last-CTA finalisation
-
-    def _workspace(self, x):
-        if not (self.fuse_finalize and x.is_cuda):
-            return None
-        ws = getattr(self, '_ws', None)
-        if ws is None or ws[0].device != x.device:
-            n = 2 * self.num_features + 4
-            ws = (torch.zeros(n, dtype=torch.float32, device=x.device),
-                  torch.zeros(n, dtype=torch.float32, device=x.device))
-            self._ws = ws
-        return ws
-
     def forward(self, x, residual=None, relu=False):
         training = self.training or (self.running_mean is None)
         momentum = 0.1 if self.momentum is None else self.momentum
@@ -130,8 +108,7 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
             self.running_mean if self.track_running_stats else None,
             self.running_var if self.track_running_stats else None,
             self.num_batches_tracked if (self.track_running_stats and training) else None,
-            residual=residual, relu=relu, training=training, momentum=momentum, eps=self.eps,
-            workspace=self._workspace(x) if training else None)
+            residual=residual, relu=relu, training=training, momentum=momentum, eps=self.eps)
 
 
 # --------------------------------------------------------------------------- #
