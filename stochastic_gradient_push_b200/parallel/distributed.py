@@ -234,7 +234,13 @@ class GossipDataParallel(Module):
         self.module = module
         self._module_copies = [self.module]
         if len(self.device_ids) > 1:
-            self._init_multi_device()
+            # the reference's DataParallel-style mode (one process driving 8 GPUs with
+            # replicate / broadcast_coalesced / reduce_add_coalesced, gossip/distributed.py:
+            # 87-99, 256-276, 523-549) is superseded by one process per GPU: intra-node
+            # replicas are ranks of the same gossip world or use nprocs_per_node > 1
+            raise NotImplementedError(
+                'single-process multi-GPU replicas are not supported: launch one rank per GPU '
+                '(torchrun --nproc-per-node N) or use nprocs_per_node for hierarchical groups')
         first_param_dtype = first_param.dtype
 
         # -- communication device / transport ------------------------------- #
@@ -340,17 +346,6 @@ class GossipDataParallel(Module):
             group = dist.new_group(masters)
         return SymmetricWorld(device, group)
 
-    def _init_multi_device(self):
-        """Legacy single-process multi-GPU replicas (reference :87-99)."""
-        from torch.nn.parallel.replicate import replicate
-        self.broadcast_bucket_size = 10 * 1024 * 1024
-        self.nccl_reduce_bucket_size = 256 * 1024 * 1024
-        self._module_copies = replicate(self.module, self.device_ids, detach=True)
-        self._module_copies[0] = self.module
-        for cmodule in self._module_copies[1:]:
-            for p, cp in zip(self.module.parameters(), cmodule.parameters()):
-                cp.requires_grad = p.requires_grad
-
     # ------------------------------------------------------------------ #
     # properties
     # ------------------------------------------------------------------ #
@@ -421,10 +416,6 @@ class GossipDataParallel(Module):
             inputs, kwargs = (inputs,), (kwargs,)
         if self.nprocs_per_node > 1:
             self._sync_params_multiprocess()
-        if len(self.device_ids) > 1:
-            self._sync_params()
-            outputs = self.parallel_apply(self._module_copies[:len(inputs)], inputs, kwargs)
-            return self.gather(outputs, self.output_device)
         return self.module(*inputs[0], **kwargs[0])
 
     def scatter(self, inputs, kwargs, device_ids):
@@ -438,21 +429,6 @@ class GossipDataParallel(Module):
     def gather(self, outputs, output_device):
         from torch.nn.parallel.scatter_gather import gather
         return gather(outputs, output_device, dim=0)
-
-    def _sync_params(self):
-        """Intra-process replica sync (legacy multi-GPU, reference :256-276)."""
-        if len(self.device_ids) <= 1:
-            return
-        from torch.cuda.comm import broadcast_coalesced
-        for tensors_of in (self.module.parameters, self.module.buffers):
-            src = [t.data for t in tensors_of()]
-            if not src:
-                continue
-            result = broadcast_coalesced(src, self.device_ids, self.broadcast_bucket_size)
-            for tensors, mod in zip(result[1:], self._module_copies[1:]):
-                dst = mod.parameters() if tensors_of == self.module.parameters else mod.buffers()
-                for t, d in zip(tensors, dst):
-                    d.data.set_(t)
 
     def _sync_params_multiprocess(self):
         """Node master -> local ranks (reference :278-296); the parameters are
@@ -657,8 +633,6 @@ class GossipDataParallel(Module):
 
     def __make_backward_hook(self):
         def hook(*unused):
-            if len(self.device_ids) > 1:
-                self._reduce_replica_grads()
             if self.nprocs_per_node > 1:
                 grads = [p.grad.data for p in self.module.parameters()
                          if p.requires_grad and p.grad is not None]
@@ -673,22 +647,6 @@ class GossipDataParallel(Module):
             # run once, at the END of this backward pass (reference :567-569)
             Variable._execution_engine.queue_callback(hook)
         return queue_hook
-
-    def _reduce_replica_grads(self):
-        from torch.cuda.comm import reduce_add_coalesced
-        all_grads = [[] for _ in self._module_copies]
-        for dev_idx, module in enumerate(self._module_copies):
-            for p in module.parameters():
-                if p.requires_grad and p.grad is not None:
-                    all_grads[dev_idx].append(p.grad.data)
-        reduced = reduce_add_coalesced(all_grads, self.output_device,
-                                       self.nccl_reduce_bucket_size)
-        for grad, red in zip(all_grads[0], reduced):
-            grad.copy_(red)
-        for module in self._module_copies[1:]:
-            for param in module.parameters():
-                if param.requires_grad:
-                    param.grad = None
 
     def __make_forward_pre_hook(self):
         def hook(*unused):

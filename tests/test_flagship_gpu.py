@@ -56,24 +56,10 @@ def test_allreduce_world1_matches_torch_sgd():
         torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.multigpu
-def test_legacy_single_process_multi_gpu_replicas():
-    """device_ids=[0, 1]: DataParallel-style replicas inside one process
-    (reference gossip/distributed.py:87-99, 231-276, 523-549)."""
+def test_single_process_multi_gpu_is_rejected_with_guidance():
     import stochastic_gradient_push_b200 as sgp
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
-    torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)).cuda(0)
-    import copy
-    ref = copy.deepcopy(net)
-    model = GossipDataParallel(net, device_ids=[0, 1], rank=0, world_size=1,
-                               graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1),
-                               transport='c10d')
-    x = torch.randn(8, 16)
-    y = model(x)                               # scattered 4 + 4 over the two GPUs
-    assert y.shape == (8, 4) and y.device.index == 0
-    torch.testing.assert_close(y, ref(x.cuda(0)), rtol=1e-5, atol=1e-5)
-    y.sum().backward()
-    ref(x.cuda(0)).sum().backward()
-    for p, q in zip(model.module.parameters(), ref.parameters()):
-        torch.testing.assert_close(p.grad, q.grad, rtol=1e-4, atol=1e-5)
+    net = torch.nn.Linear(4, 4).cuda(0)
+    with pytest.raises(NotImplementedError, match='one rank per GPU'):
+        GossipDataParallel(net, device_ids=[0, 1], rank=0, world_size=1,
+                           graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1))
