@@ -206,11 +206,14 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
         if i % 100 == 0:
             update_learning_rate(args, optimizer, epoch, itr=i, itr_per_epoch=len(loader))
         if trainer is not None:
-            # whole step = one CUDA-graph replay (forward+backward+fused gossip kernel)
+            # whole step = one CUDA-graph replay (forward+backward+fused gossip kernel);
+            # the metrics are computed on the trainer's stream, before the next replay
+            # can overwrite the static output buffers
             trainer.step(batch, target)
-            with torch.cuda.stream(trainer.stream):
-                output, loss = trainer.static_out, trainer.static_loss
-                target = trainer.static_tgt
+            with torch.cuda.stream(trainer.stream), torch.no_grad():
+                p1, p5 = accuracy(trainer.static_out, trainer.static_tgt, topk=(1, 5))
+                pending.append((torch.stack([trainer.static_loss.float().reshape(()),
+                                             p1[0], p5[0]]), batch.size(0)))
         else:
             with _autocast(args):
                 output = model(batch)
@@ -220,10 +223,10 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
             optimizer.zero_grad()
             if not args.overlap and not args.all_reduce:
                 model.transfer_params()
-        with torch.no_grad():
-            p1, p5 = accuracy(output, target, topk=(1, 5))
-            pending.append((torch.stack([loss.detach().float().reshape(()), p1[0], p5[0]]),
-                            batch.size(0)))
+            with torch.no_grad():
+                p1, p5 = accuracy(output, target, topk=(1, 5))
+                pending.append((torch.stack([loss.detach().float().reshape(()), p1[0], p5[0]]),
+                                batch.size(0)))
         t_nn = time.time() - t_nn
         if ignore == 0:
             data_meter.update(t_data)
@@ -235,6 +238,8 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
 
         last = (limit not in (None, -1) and i + 1 == limit)
         if i % args.print_freq == 0 or last:
+            if trainer is not None:
+                trainer.stream.synchronize()
             vals = torch.stack([v for v, _ in pending]).cpu()      # ONE sync per interval
             for (l, a1, a5), (_, n) in zip(vals.tolist(), pending):
                 losses.update(l, n)
@@ -244,6 +249,8 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
             csv.train_row(epoch, i, batch_meter, nn_meter, data_meter, losses, top1, top5)
         if last:
             break
+    if trainer is not None:
+        torch.cuda.synchronize()       # eval / checkpointing run on the default stream
     if pending:
         vals = torch.stack([v for v, _ in pending]).cpu()
         for (l, a1, a5), (_, n) in zip(vals.tolist(), pending):
