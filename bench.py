@@ -41,7 +41,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--algo', default='sgp', choices=['sgp', 'osgp', 'dpsgd', 'ar'])
+    ap.add_argument('--algo', default='sgp', choices=['sgp', 'osgp', 'dpsgd', 'ar', 'adpsgd'])
     ap.add_argument('--batch-size', '--batch_size', dest='batch_size', type=int, default=256,
                     help='per-agent batch; 256 = every shipped job script of the reference '
                          '(job_scripts/submit_*.sh: --batch_size 256 per gossip agent); one agent '
@@ -141,6 +141,8 @@ def run_ours(args):
     models.init_imagenet_in_1hr(net)
     net = net.to(dev).to(memory_format=torch.channels_last)
 
+    if args.algo == 'adpsgd':
+        return run_adpsgd(args, net, rank, world, dev, amp)
     if args.algo == 'ar':
         from stochastic_gradient_push_b200.parallel.allreduce import AllReduceDataParallel, ARTrainer
         model = AllReduceDataParallel(net)
@@ -247,6 +249,87 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_adpsgd(args, net, rank, world, dev, amp):
+    """AD-PSGD (BilatGossipDataParallel): asynchronous by construction, so the step is
+    the reference-style eager loop (forward, backward hook = push grads + pull model,
+    local step); gossip + the gossip-side fused SGD run on the low-priority stream."""
+    import torch
+    import torch.distributed as dist
+    import stochastic_gradient_push_b200 as sgp
+    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel
+    bs, K, W = args.batch_size, args.steps, args.warmup
+    lr = 0.1 * bs * world / 256
+    model = BilatGossipDataParallel(net, rank=rank, world_size=world,
+                                    graph_class=sgp.DynamicBipartiteExponentialGraph,
+                                    mixing_class=sgp.UniformMixing, lr=lr, momentum=0.9,
+                                    weight_decay=1e-4, nesterov=True, verbose=False,
+                                    heartbeat_timeout=60)
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    crit = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1234 + rank)
+    pool = [(torch.randn(bs, 3, 224, 224, generator=g).pin_memory(),
+             torch.randint(0, 1000, (bs,), generator=g).pin_memory()) for _ in range(4)]
+    loss_host = torch.zeros(K + W + 8).pin_memory()
+    model.train()
+    model.enable_gossip()
+
+    def step(i):
+        x, y = pool[i % 4]
+        x = x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        y = y.to(dev, non_blocking=True)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp is not None):
+            loss = crit(model(x).float(), y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        loss_host[i:i + 1].copy_(loss.detach().view(1), non_blocking=True)
+
+    for i in range(max(W, 5)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0))) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rounds0 = model.rounds_completed
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    rounds = torch.tensor([float(model.rounds_completed - rounds0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rounds, op=dist.ReduceOp.MIN)
+    ms = ms.item()
+    value = bs * world * K / (ms / 1e3)
+    model.disable_gossip()
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'resnet50_adpsgd_images_per_sec', 'value': round(value, 2), 'unit': 'images/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': round(ms / K, 4),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+            'data': 'synthetic', 'impl': 'ours', 'value_is_e2e': True,
+            'config': {'model': args.model, 'algorithm': 'adpsgd', 'graph': 'dynamic bipartite exponential',
+                       'per_gpu_batch': bs, 'global_batch': bs * world, 'image': '3x224x224',
+                       'parallelism': 'dp%d-bilateral-gossip' % world, 'cuda_graph': False,
+                       'gossip_rounds_in_timed_region_min_over_ranks': int(rounds.item()),
+                       'l2': 'per-step working set exceeds the 126 MB L2; no explicit flush'},
+            'clocks': clocks,
+            'e2e': {'value': round(value, 2), 'unit': 'images/s',
+                    'h2d_bytes_per_step': pool[0][0].numel() * 4 + bs * 8, 'd2h_bytes_per_step': 4},
+            'gpu_launches': None}))
+    if world > 1:
+        dist.barrier()
+    model.shutdown()
+    if world > 1:
         dist.destroy_process_group()
 
 
