@@ -54,7 +54,7 @@ class BilatGossipDataParallel(Module):
                  weight_decay=1e-4, nesterov=True, verbose=True,
                  network_interface_type=None, tcp_interface_name=None,
                  transport='auto', poll_interval=2e-4, gossip_grid=32,
-                 heartbeat_timeout=300.0):
+                 heartbeat_timeout=300.0, max_rounds_per_update=4):
         super(BilatGossipDataParallel, self).__init__()
         first = next(module.parameters())
         on_cuda = first.is_cuda
@@ -98,6 +98,11 @@ class BilatGossipDataParallel(Module):
         self.logger = make_logger(rank, verbose)
         self.gossip_enable = True
         self._poll = float(poll_interval)
+        # the reference's gossip process averages as fast as it can, even when no new
+        # gradient arrived; on NVLink that is ~18 rounds (1.8 GB of pulls) per training
+        # step competing with the model for HBM and SMs.  Bound it (None = unbounded).
+        self.max_rounds_per_update = max_rounds_per_update
+        self._rounds_since_update = 0
         self._timeout_s = float(heartbeat_timeout)
 
         # graph / mixing are given as CLASSES (instantiated here, like the
@@ -310,9 +315,17 @@ class BilatGossipDataParallel(Module):
                     self.gossip_flat.copy_(x)
                     self.momentum_flat.copy_(m)
             self.grads_applied += 1
+            self._rounds_since_update = 0
             self.train_write_flag.clear()
             self.gossip_read_flag.set()
             self.model_meter.update(time.time() - bt)
+
+    def _throttled(self, round_in_flight):
+        """True when this rank has done enough rounds since its last gradient and
+        is not in the middle of one (a round in flight is always completed)."""
+        k = self.max_rounds_per_update
+        return (k is not None) and (not round_in_flight) and (self._rounds_since_update >= k) \
+            and self.training
 
     def _loop_kernels(self):
         cfg = dict(self.dist_config)
@@ -324,7 +337,7 @@ class BilatGossipDataParallel(Module):
             if not self.gossip_enable_flag.wait(timeout=0.05):
                 continue
             self._apply_pending(cfg)
-            if alone:
+            if alone or self._throttled(published):
                 time.sleep(self._poll)
                 continue
             bt = time.time()
@@ -345,6 +358,7 @@ class BilatGossipDataParallel(Module):
                 e.check()
                 published = False
                 self.rounds_completed += 1
+                self._rounds_since_update += 1
                 self.gossip_meter.update(time.time() - bt)
             else:
                 time.sleep(self._poll)
@@ -385,7 +399,7 @@ class BilatGossipDataParallel(Module):
             if not self.gossip_enable_flag.wait(timeout=0.05):
                 continue
             self._apply_pending(cfg)
-            if alone:
+            if alone or self._throttled(sent is not None):
                 time.sleep(self._poll)
                 continue
             if sent is None:
@@ -411,6 +425,7 @@ class BilatGossipDataParallel(Module):
             g.refresh_peers_()
             rnd += 1
             self.rounds_completed += 1
+            self._rounds_since_update += 1
             self.gossip_meter.update(time.time() - t_round)
 
     # ------------------------------------------------------------------ #
