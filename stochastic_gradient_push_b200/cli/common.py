@@ -347,34 +347,3 @@ def init_model(args):
     if args.channels_last and args.device == 'cuda':
         net = net.to(memory_format=torch.channels_last)
     return net
-
-
-class DeviceTimer(object):
-    """CUDA-event interval timer with deferred read-out: ``lap()`` records an
-    event, ``flush()`` converts all completed intervals into seconds (one sync
-    per print interval instead of three ``.item()`` syncs per iteration,
-    ``gossip_sgd.py:405-407``)."""
-
-    def __init__(self, enabled):
-        self.enabled = enabled
-        self.events = []
-        self.host = time.time()
-
-    def lap(self):
-        if self.enabled:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            self.events.append(ev)
-        else:
-            self.events.append(time.time())
-
-    def flush(self):
-        if len(self.events) < 2:
-            return []
-        if self.enabled:
-            self.events[-1].synchronize()
-            out = [a.elapsed_time(b) / 1e3 for a, b in zip(self.events[:-1], self.events[1:])]
-        else:
-            out = [b - a for a, b in zip(self.events[:-1], self.events[1:])]
-        self.events = self.events[-1:]
-        return out

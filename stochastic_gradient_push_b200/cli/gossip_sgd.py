@@ -30,7 +30,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import common
-from .common import (CSVLog, DeviceTimer, Meter, accuracy, build_parser, finalize_args,
+from .common import (CSVLog, Meter, accuracy, build_parser, finalize_args,
                      fresh_state, init_model, make_dataloader, update_learning_rate,
                      update_peers_per_itr, update_state)
 from ..experiment import ClusterManager, make_logger

@@ -67,7 +67,6 @@ class _KernelBackend(object):
         from ..ops.peer_mix import GossipEngine
         self.owner = owner
         self.arena = arena
-        dev = arena.flat.device
         self.shadow = None
         if compute_dtype is not None and compute_dtype != torch.float32:
             assert compute_dtype == torch.bfloat16, 'compute copies are bf16'
@@ -79,12 +78,10 @@ class _KernelBackend(object):
         self.gather_event = None
         self.residual_pending = False       # a gather finished/launched and is not folded yet
         self.sgd_pending = False            # FusedGossipSGD.step() deferred into next launch
-        self.has_sgd_buffers = False
 
     # optimizer buffers are attached lazily by FusedGossipSGD
     def attach_sgd(self, grad_flat, momentum_flat):
         self.engine.set_sgd_buffers(grad_flat, momentum_flat)
-        self.has_sgd_buffers = True
 
 
 class _C10dBackend(object):

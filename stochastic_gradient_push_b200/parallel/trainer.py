@@ -68,7 +68,6 @@ class GossipTrainer(object):
         self._prefetched = False
         self._loss_ring = None
         self._loss_slot = 0
-        self.launches_per_step = None
 
     # ------------------------------------------------------------------ #
     def _autocast(self):
@@ -84,20 +83,14 @@ class GossipTrainer(object):
         self.static_loss.copy_(loss.detach())
         self.static_out = out.detach()
 
-    def _gossip_kernels(self, first: bool):
-        """The gossip / optimizer launches of one step.  ``first``: no gradient
-        and no residual exist yet (only relevant for overlap)."""
-        e = self.engine
-        if not self.gossip or not self.model.gossip_enable:
-            e.local(sgd=True)
-        elif self.overlap:
-            raise RuntimeError('overlap handled in _step_overlap')
-        else:
-            e.mix(sgd=True)
-
     def _step_sync(self):
+        """forward/backward, then ONE kernel: SGD + publish + pull + mix + de-bias
+        (SGD only when there is nobody to gossip with)."""
         self._fwd_bwd()
-        self._gossip_kernels(False)
+        if self.gossip and self.model.gossip_enable:
+            self.engine.mix(sgd=True)
+        else:
+            self.engine.local(sgd=True)
 
     def _step_overlap(self, first: bool):
         """publish(k) -> [gather(k) on gossip_stream || fwd/bwd(k)] ; the SGD of

@@ -3,11 +3,10 @@ Running statistics meter (API parity: ``gossip/utils/metering.py:13-80``,
 duplicated in the reference as ``experiment_utils/metering.py``).
 
 val / avg / sum / count / std (sample std from running sums) and, when
-``stateful``, the full history plus mean-absolute-deviation.  The MAD is
-maintained from the stored history in O(n) only when it is *read* by
-``__str__``/``mad`` callers would be cheaper, but checkpoints store
-``__dict__`` verbatim (``gossip_sgd.py:214-216``) so the fields are kept as
-plain attributes and refreshed on update like the reference.
+``stateful``, the full history plus the mean absolute deviation.  All
+statistics are plain attributes refreshed on every ``update`` because
+checkpoints store ``meter.__dict__`` verbatim and re-hydrate a meter from it
+(``gossip_sgd.py:214-216, 257-259``).
 """
 
 
