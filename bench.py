@@ -50,6 +50,8 @@ def parse():
     ap.add_argument('--model', default='resnet50')
     ap.add_argument('--ppi', type=int, default=1)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--autocast', action='store_true',
+                    help='bf16 via torch.autocast instead of the bf16 shadow-weight twin')
     ap.add_argument('--skip-e2e', action='store_true')
     return ap.parse_args()
 
@@ -159,7 +161,9 @@ def run_ours(args):
             graph_name = 'n-peer dynamic directed exponential'
         model = GossipDataParallel(net, graph=graph, push_sum=(args.algo != 'dpsgd'),
                                    overlap=(args.algo == 'osgp'), rank=rank, world_size=world,
-                                   verbose=False, heartbeat_timeout=60)
+                                   verbose=False, heartbeat_timeout=60,
+                                   compute_dtype=(torch.bfloat16 if (amp is not None and not args.autocast)
+                                                  else None))
         opt = FusedGossipSGD(model, lr=0.1 * bs * world / 256, momentum=0.9,
                              weight_decay=1e-4, nesterov=True)
         trainer = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=not args.no_graph)
@@ -240,6 +244,8 @@ def run_ours(args):
                        'peers_per_itr': args.ppi, 'per_gpu_batch': bs, 'global_batch': bs * world,
                        'image': '3x224x224', 'parallelism': 'dp%d-gossip' % world,
                        'master_weights': 'fp32 flat arena', 'layout': 'NHWC',
+                       'bf16_path': ('autocast' if (args.autocast or args.algo == 'ar') else
+                                     'shadow weights written by the gossip kernel'),
                        'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (activations+weights > 1 GB) exceeds the '
                              '126 MB L2; no explicit flush'},

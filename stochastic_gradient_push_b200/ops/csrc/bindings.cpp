@@ -185,6 +185,18 @@ public:
         grad_keep_ = g;
     }
 
+    void set_grad2(c10::optional<torch::Tensor> g2)
+    {
+        if (g2.has_value() && g2->defined()) {
+            TORCH_CHECK(g2->numel() == args_.n && g2->scalar_type() == torch::kFloat32 && g2->is_contiguous());
+            args_.g2 = g2->data_ptr<float>();
+            grad2_keep_ = *g2;
+        } else {
+            args_.g2 = nullptr;
+            grad2_keep_ = torch::Tensor();
+        }
+    }
+
     void set_sgd_buffers(torch::Tensor g, torch::Tensor m)
     {
         set_grad(g);
@@ -279,6 +291,7 @@ private:
     std::vector<torch::Tensor> keep_;
     std::vector<torch::Tensor> sched_keep_;
     torch::Tensor grad_keep_;
+    torch::Tensor grad2_keep_;
     torch::Tensor mom_keep_;
 };
 
@@ -360,6 +373,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("set_schedule", &GossipContext::set_schedule)
         .def("set_grad", &GossipContext::set_grad)
         .def("set_sgd_buffers", &GossipContext::set_sgd_buffers)
+        .def("set_grad2", &GossipContext::set_grad2)
         .def("set_timeout", &GossipContext::set_timeout)
         .def("set_segments", &GossipContext::set_segments)
         .def("segments", &GossipContext::segments)

@@ -94,6 +94,9 @@ struct SgpArgs {
     // local buffers (length n, n % SGP_CHUNK == 0)
     float*               z;          // de-biased parameters (fp32 master)
     void*                g;          // gradient (fp32 / bf16) or null
+    float*               g2;         // optional 2nd gradient buffer (fp32), added to g:
+                                     //   bf16 grads of the bf16 compute weights + fp32 grads
+                                     //   of the fp32 (BatchNorm) parameters, same layout
     float*               m;          // momentum or null
     __nv_bfloat16*       shadow;     // bf16 copy of z or null
     float*               residual;   // overlap residual or null

@@ -169,6 +169,10 @@ sgp_step_kernel(const SgpArgs a)
                         else
                             g[u] = ld_once_f4(reinterpret_cast<const float4*>(
                                        reinterpret_cast<const float*>(a.g) + i), pol_first);
+                        if (a.g2 != nullptr) {
+                            const float4 h = ld_once_f4(reinterpret_cast<const float4*>(a.g2 + i), pol_first);
+                            g[u].x += h.x; g[u].y += h.y; g[u].z += h.z; g[u].w += h.w;
+                        }
                         m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
                     }
                     if (flags & SGP_F_FOLD_RES)
@@ -193,6 +197,8 @@ sgp_step_kernel(const SgpArgs a)
                             else
                                 st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g) + i),
                                       make_float4(0.f, 0.f, 0.f, 0.f));
+                            if (a.g2 != nullptr)
+                                st_f4(reinterpret_cast<float4*>(a.g2 + i), make_float4(0.f, 0.f, 0.f, 0.f));
                         }
                     }
                     if (flags & SGP_F_FOLD_RES) {

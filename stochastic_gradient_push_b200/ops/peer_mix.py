@@ -158,9 +158,13 @@ class GossipEngine(object):
         self.grad = grad
         self.ctx.set_grad(grad)
 
-    def set_sgd_buffers(self, grad: torch.Tensor, momentum: torch.Tensor):
-        self.grad, self.momentum = grad, momentum
+    def set_sgd_buffers(self, grad: torch.Tensor, momentum: torch.Tensor, grad2=None):
+        """``grad2``: optional fp32 buffer (same layout) that is ADDED to ``grad``:
+        with bf16 compute weights the convolution/linear gradients arrive in the bf16
+        buffer and the BatchNorm gradients in the fp32 one (each zero elsewhere)."""
+        self.grad, self.momentum, self.grad2 = grad, momentum, grad2
         self.ctx.set_sgd_buffers(grad, momentum)
+        self.ctx.set_grad2(grad2)
 
     # -- launches ------------------------------------------------------------ #
     def _common(self, sgd, zero_grad, in_numerator=False):

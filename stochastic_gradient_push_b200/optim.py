@@ -48,7 +48,21 @@ class FusedGossipSGD(object):
             self.momentum_flat[dtype] = arena.new_buffer(dtype=torch.float32
                                                          if dtype != torch.float64 else dtype)
             arena.bind_grads(model._params_by_dtype[dtype], self.grad_flat[dtype])
-        if model._kernel is not None:
+        self.grad_lo = None
+        if model._kernel is not None and model._twin:
+            # bf16 compute twin: its conv/linear gradients accumulate into a bf16 flat
+            # buffer, the normalisation gradients (and anything computed through the fp32
+            # master module) into the fp32 one; the kernel adds the two
+            arena = self._arenas[torch.float32]
+            self.grad_lo = arena.new_buffer(dtype=torch.bfloat16)
+            lo_views = arena.views_of(self.grad_lo)
+            hi_views = arena.views_of(self.grad_flat[torch.float32])
+            for p, lo, hi in zip(model._twin[0].parameters(), lo_views, hi_views):
+                if p.requires_grad:
+                    p.grad = lo if p.dtype == torch.bfloat16 else hi
+            model._kernel.attach_sgd(self.grad_lo, self.momentum_flat[torch.float32],
+                                     grad2=self.grad_flat[torch.float32])
+        elif model._kernel is not None:
             model._kernel.attach_sgd(self.grad_flat[torch.float32],
                                      self.momentum_flat[torch.float32])
         model._fused_optimizer = self
@@ -89,6 +103,8 @@ class FusedGossipSGD(object):
             return
         for g in self.grad_flat.values():
             g.zero_()
+        if self.grad_lo is not None:
+            self.grad_lo.zero_()
 
     def state_dict(self):
         self.model._flush_pending()

@@ -80,8 +80,8 @@ class _KernelBackend(object):
         self.sgd_pending = False            # FusedGossipSGD.step() deferred into next launch
 
     # optimizer buffers are attached lazily by FusedGossipSGD
-    def attach_sgd(self, grad_flat, momentum_flat):
-        self.engine.set_sgd_buffers(grad_flat, momentum_flat)
+    def attach_sgd(self, grad_flat, momentum_flat, grad2=None):
+        self.engine.set_sgd_buffers(grad_flat, momentum_flat, grad2)
 
 
 class _C10dBackend(object):
@@ -322,6 +322,9 @@ class GossipDataParallel(Module):
             else:
                 self._c10d = _C10dBackend(self, self._arenas, graph, mixing, comm_device)
         self.transport = 'nvlink' if self._kernel is not None else 'c10d'
+        self._twin = []          # [bf16 compute twin] (a list so it is not a registered submodule)
+        if self._kernel is not None and self._kernel.shadow is not None:
+            self._twin.append(self._build_compute_twin())
         self.dist_config['gossipers'] = {
             dtype: _GossiperView(self, dtype) for dtype in self._arenas}
         self.gossip_ps_factor.fill_(mixing.scalar_weights()[0])
@@ -333,6 +336,36 @@ class GossipDataParallel(Module):
     # ------------------------------------------------------------------ #
     # construction helpers
     # ------------------------------------------------------------------ #
+    def _build_compute_twin(self):
+        """bf16 twin of ``self.module`` for the forward/backward pass.
+
+        Its convolution / linear parameters are bf16 views of the SHADOW arena that
+        the gossip kernel rewrites every step (``SGP_F_SHADOW``), so no cast kernel
+        ever runs (autocast re-casts all 54 weight tensors forward and their gradients
+        backward, every step); its normalisation parameters ARE the fp32 master views
+        and its buffers (running statistics) ARE the master module's buffers."""
+        import copy
+        from torch.nn.modules.batchnorm import _NormBase
+        arena = self._arenas[torch.float32]
+        twin = copy.deepcopy(self.module)
+        norm_ids = set(id(p) for m in twin.modules() if isinstance(m, _NormBase)
+                       for p in m.parameters(recurse=False))
+        shadow_views = arena.views_of(self._kernel.shadow)
+        with torch.no_grad():
+            for p, v_master, v_shadow in zip(twin.parameters(), arena.views, shadow_views):
+                p.data = v_master if id(p) in norm_ids else v_shadow
+                p.grad = None
+        for m_t, m_m in zip(twin.modules(), self.module.modules()):
+            for name in list(m_m._buffers):
+                m_t._buffers[name] = m_m._buffers[name]
+        return twin
+
+    @property
+    def compute_module(self):
+        """The module the fast path runs: the bf16 twin if ``compute_dtype`` was given,
+        else the wrapped module itself."""
+        return self._twin[0] if self._twin else self.module
+
     def _make_symmetric_world(self, world_size, device):
         from .symmetric import LocalWorld, SymmetricWorld
         if world_size == 1:

@@ -76,9 +76,17 @@ class GossipTrainer(object):
         return torch.autocast('cuda', dtype=self.amp_dtype)
 
     def _fwd_bwd(self):
-        with self._autocast():
-            out = self.model.module(self.static_in)
+        twin = getattr(self.model, '_twin', None)
+        if twin:
+            # bf16 twin: weights already live in bf16 (shadow arena), input buffer is bf16
+            net = twin[0]
+            net.train(self.model.module.training)
+            out = net(self.static_in)
             loss = self.criterion(out.float(), self.static_tgt)
+        else:
+            with self._autocast():
+                out = self.model.module(self.static_in)
+                loss = self.criterion(out.float(), self.static_tgt)
         loss.backward()
         self.static_loss.copy_(loss.detach())
         self.static_out = out.detach()
@@ -121,7 +129,8 @@ class GossipTrainer(object):
             return
         fmt = torch.channels_last if (self.channels_last and batch.dim() == 4) \
             else torch.contiguous_format
-        self.static_in = torch.empty(batch.shape, dtype=batch.dtype, device=self.device
+        in_dtype = torch.bfloat16 if getattr(self.model, '_twin', None) else batch.dtype
+        self.static_in = torch.empty(batch.shape, dtype=in_dtype, device=self.device
                                      ).contiguous(memory_format=fmt)
         self.static_tgt = torch.empty(target.shape, dtype=target.dtype, device=self.device)
         # staging keeps the HOST layout (plain pinned memcpy); the device-side

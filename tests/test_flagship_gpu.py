@@ -63,3 +63,45 @@ def test_single_process_multi_gpu_is_rejected_with_guidance():
     with pytest.raises(NotImplementedError, match='one rank per GPU'):
         GossipDataParallel(net, device_ids=[0, 1], rank=0, world_size=1,
                            graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1))
+
+
+def _train_tiny(compute_dtype, amp, steps=6, graph=False):
+    import stochastic_gradient_push_b200 as sgp
+    from stochastic_gradient_push_b200 import models
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(3)
+    net = models.TinyConvNet(width=32).to(dev).to(memory_format=torch.channels_last)
+    model = GossipDataParallel(net, graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1), rank=0,
+                               world_size=1, heartbeat_timeout=20, compute_dtype=compute_dtype)
+    opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    tr = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=graph, warmup_iters=2)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(32, 3, 32, 32, generator=g).pin_memory()
+    y = torch.randint(0, 10, (32,), generator=g).pin_memory()
+    slots = [tr.step(x, y) for _ in range(steps)]
+    tr.finish()
+    return model, [float(tr.loss_ring[s]) for s in slots]
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_bf16_shadow_twin_tracks_the_autocast_path(graph):
+    m_twin, l_twin = _train_tiny(torch.bfloat16, torch.bfloat16, graph=graph)
+    m_auto, l_auto = _train_tiny(None, torch.bfloat16, graph=graph)
+    assert m_twin.compute_module is not m_twin.module and m_auto.compute_module is m_auto.module
+    # the shadow is exactly the bf16 rounding of the fp32 master arena, every step
+    torch.testing.assert_close(m_twin.compute_shadow.float(), m_twin.arena.flat.bfloat16().float(),
+                               rtol=0, atol=0)
+    # BN parameters of the twin ARE the master tensors; running statistics are shared
+    import torch.nn as nn
+    for a, b in zip(m_twin.compute_module.modules(), m_twin.module.modules()):
+        if isinstance(a, nn.BatchNorm2d):
+            assert a.weight.data_ptr() == b.weight.data_ptr()
+            assert a.running_mean.data_ptr() == b.running_mean.data_ptr()
+    assert l_twin[-1] < l_twin[0]
+    for lt, la in zip(l_twin, l_auto):
+        assert abs(lt - la) < 0.05 * max(1.0, abs(la))
+    rel = (m_twin.arena.flat - m_auto.arena.flat).norm() / m_auto.arena.flat.norm()
+    assert rel.item() < 2e-2
