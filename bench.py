@@ -339,8 +339,23 @@ def run_adpsgd(args, net, rank, world, dev, amp):
         dist.destroy_process_group()
 
 
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` without a launcher: start one rank per GPU ourselves."""
+    import socket
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node',
+           str(args.gpus), '--master-addr', '127.0.0.1', '--master-port', str(port),
+           os.path.abspath(__file__)] + sys.argv[1:]
+    sys.exit(subprocess.call(cmd))
+
+
 def main():
     args = parse()
+    if args.gpus > 1 and 'RANK' not in os.environ:
+        relaunch_under_torchrun(args)
     if args.impl == 'reference':
         sys.path.insert(0, os.path.join(ROOT, 'baseline'))
         try:
