@@ -24,7 +24,7 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
-from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC
+from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC, stem_conv
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -116,7 +116,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x), relu=True))
+        x = self.maxpool(self.bn1(stem_conv(self.conv1, x), relu=True))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)

@@ -202,8 +202,57 @@ static torch::Tensor maxpool_backward(torch::Tensor dy, torch::Tensor code, int 
     return dx;
 }
 
+// ---------------------------------------------------------------------------
+// ResNet stem convolution (3 -> 64, 7x7 / 2, pad 3), NHWC bf16
+// ---------------------------------------------------------------------------
+extern "C" {
+cudaError_t stem_launch_fwd(const void* x, const void* w, void* y, int N, int H, int W, int OH, int OW,
+                            cudaStream_t st);
+cudaError_t stem_launch_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W,
+                              int OH, int OW, cudaStream_t st);
+}
+
+static bool stem_can_fuse(const torch::Tensor& x, const torch::Tensor& w)
+{
+    return x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == torch::kBFloat16
+        && x.is_contiguous(at::MemoryFormat::ChannelsLast)
+        && w.dim() == 4 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 7 && w.size(3) == 7
+        && w.scalar_type() == torch::kBFloat16 && w.is_contiguous(at::MemoryFormat::ChannelsLast)
+        && x.size(2) >= 7 && x.size(3) >= 7;
+}
+
+static torch::Tensor stem_forward(torch::Tensor x, torch::Tensor w)
+{
+    TORCH_CHECK(stem_can_fuse(x, w), "stem_forward: unsupported tensors");
+    const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+    const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto y = torch::empty({N, 64, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    BN_CHECK(stem_launch_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, OH, OW,
+                             at::cuda::getCurrentCUDAStream()));
+    return y;
+}
+
+// returns dW as an fp32 [64, 3, 7, 7] tensor in channels_last layout
+static torch::Tensor stem_wgrad(torch::Tensor x, torch::Tensor dy)
+{
+    TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && x.is_contiguous(at::MemoryFormat::ChannelsLast));
+    TORCH_CHECK(dy.scalar_type() == torch::kBFloat16 && dy.size(1) == 64);
+    if (!dy.is_contiguous(at::MemoryFormat::ChannelsLast)) dy = dy.contiguous(at::MemoryFormat::ChannelsLast);
+    const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+    const int OH = (int)dy.size(2), OW = (int)dy.size(3);
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto acc = torch::zeros({64, 7, 7, 3}, x.options().dtype(torch::kFloat32));
+    BN_CHECK(stem_launch_wgrad(x.data_ptr(), dy.data_ptr(), acc.data_ptr<float>(), N, H, W, OH, OW,
+                               at::cuda::getCurrentCUDAStream()));
+    return acc.permute({0, 3, 1, 2});
+}
+
 void bind_bn(py::module& mod)
 {
+    mod.def("stem_can_fuse", &stem_can_fuse);
+    mod.def("stem_forward", &stem_forward);
+    mod.def("stem_wgrad", &stem_wgrad);
     mod.def("pool_can_fuse", &pool_can_fuse);
     mod.def("maxpool_forward", &maxpool_forward);
     mod.def("maxpool_backward", &maxpool_backward);

@@ -185,3 +185,47 @@ def test_maxpool_ties_route_to_first_max():
     MaxPool2dNHWC(3, 2, 1)(x1).sum().backward()
     torch.nn.functional.max_pool2d(x2, 3, 2, 1).sum().backward()
     torch.testing.assert_close(x1.grad, x2.grad, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize('shape', [(4, 3, 64, 64), (3, 3, 224, 224), (2, 3, 70, 90), (1, 3, 33, 47)])
+def test_stem_conv_matches_conv2d(shape):
+    """tensor-core stem convolution (fwd + wgrad) vs F.conv2d in fp32 on the same
+    bf16-rounded operands."""
+    from stochastic_gradient_push_b200.ops.fused_bn import stem_conv
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(shape, device='cuda').bfloat16().contiguous(memory_format=torch.channels_last)
+    y = stem_conv(conv, x)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    wq = conv.weight.detach().bfloat16().float().requires_grad_(True)
+    y_ref = torch.nn.functional.conv2d(x.float(), wq, None, 2, 3)
+    assert y.shape == y_ref.shape
+    torch.testing.assert_close(y.float(), y_ref, rtol=2e-2, atol=2e-2)
+    dy = torch.randn_like(y_ref).bfloat16()
+    y.backward(dy)
+    y_ref.backward(dy.float())
+    scale = wq.grad.abs().max().item()
+    assert (conv.weight.grad - wq.grad).abs().max().item() < 1e-2 * scale
+
+
+def test_stem_conv_inside_resnet_training_step():
+    """the whole bf16 twin path (stem conv + fused BN + max-pool) produces finite,
+    decreasing losses -- see test_flagship_gpu for the trainer-level checks."""
+    from stochastic_gradient_push_b200.models import resnet50
+    from stochastic_gradient_push_b200.ops import fused_bn
+    net = resnet50().cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(8, 3, 96, 96, device='cuda').contiguous(memory_format=torch.channels_last)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        y1 = net(x)
+    fused_bn.FORCE_REFERENCE = True
+    try:
+        net2 = resnet50().cuda().to(memory_format=torch.channels_last)
+        net2.load_state_dict(net.state_dict())
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            s1 = fused_bn.stem_conv(net2.conv1, x)          # reference path: cuDNN
+    finally:
+        fused_bn.FORCE_REFERENCE = False
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        s2 = fused_bn.stem_conv(net.conv1, x)
+    torch.testing.assert_close(s2.float(), s1.float(), rtol=3e-2, atol=3e-2)
+    assert torch.isfinite(y1).all()

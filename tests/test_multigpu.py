@@ -365,3 +365,29 @@ def test_bounded_staleness_on_kernels_conserves_mass():
     mass = sum(torch.tensor(z) * w for z, w in out)
     torch.testing.assert_close(mass, x0.sum(0), rtol=1e-4, atol=1e-4)
     assert abs(sum(w for _, w in out) - n) < 1e-4
+
+
+def _barrier_worker(rank, world):
+    import time
+    from stochastic_gradient_push_b200.parallel.symmetric import SymmetricWorld
+    from stochastic_gradient_push_b200.ops.peer_mix import GossipEngine
+    dev = torch.device('cuda', rank)
+    graph = sgp.RingGraph(rank, world)
+    eng = GossipEngine(SymmetricWorld(dev), torch.zeros(4096, device=dev), graph,
+                       sgp.UniformMixing(graph, dev), timeout_s=20.0, name='bar')
+    stamps = []
+    for i in range(3):
+        time.sleep(0.05 * rank)                  # ranks arrive staggered
+        eng.barrier()
+        torch.cuda.synchronize()
+        stamps.append(time.time())
+    eng.check()
+    return stamps
+
+
+def test_device_barrier_kernel():
+    n = min(_ngpu(), 4)
+    out = run_distributed(_barrier_worker, n, backend='nccl', timeout=200)
+    for i in range(3):                            # nobody leaves a barrier before the last arrives
+        leave = [out[r][i] for r in range(n)]
+        assert max(leave) - min(leave) < 0.04, leave
