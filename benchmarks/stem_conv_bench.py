@@ -37,8 +37,10 @@ dy = torch.randn_like(y)
 wr = w.clone().requires_grad_(True)
 t_cudnn_f = timed(lambda: F.conv2d(x, w, None, 2, 3))
 t_cudnn_fb = timed(lambda: torch.autograd.grad(F.conv2d(x, wr, None, 2, 3), [wr], dy))
+t_cudnn_w = timed(lambda: torch.ops.aten.convolution_backward(
+    dy, x, w, None, [2, 2], [3, 3], [1, 1], False, [0, 0], 1, [False, True, False]))
 t_ours_f = timed(lambda: C.stem_forward(x, w))
 t_ours_b = timed(lambda: C.stem_wgrad(x, dy))
 io = (x.numel() + y.numel()) * 2 / 1e6
-print('stem conv batch %d: cuDNN fwd %.3f ms, fwd+wgrad %.3f ms | ours fwd %.3f ms (%.2f TB/s), wgrad %.3f ms'
-      % (B, t_cudnn_f, t_cudnn_fb, t_ours_f, io / t_ours_f / 1e3, t_ours_b))
+print('stem conv batch %d: cuDNN fwd %.3f ms, wgrad-only %.3f ms, fwd+wgrad %.3f ms | ours fwd %.3f ms (%.2f TB/s), wgrad %.3f ms'
+      % (B, t_cudnn_f, t_cudnn_w, t_cudnn_fb, t_ours_f, io / t_ours_f / 1e3, t_ours_b))

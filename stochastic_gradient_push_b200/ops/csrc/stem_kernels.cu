@@ -28,6 +28,11 @@
 #define ST_KP 160                    // K padded to 10 mma k-steps
 #define ST_CO 64
 #define ST_WPITCH 168                // weight row pitch in smem (bank-conflict padding)
+// forward-only K layout: every kh row (7*3 = 21 taps) is padded to 24, so that the k pairs
+// an mma register holds (2m, 2m+1) are ADJACENT, 4-byte aligned elements of the patch
+// (32-bit shared loads instead of two 16-bit loads + a pack).  7 * 24 = 168 -> 176 (11 steps)
+#define ST_KF 176
+#define ST_WFPITCH 184
 
 namespace {
 
@@ -74,19 +79,22 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
                 uint16_t* __restrict__ y, int N, int H, int W, int OH, int OW)
 {
-    __shared__ __align__(16) uint16_t s_w[ST_CO * ST_WPITCH];        // [co][k]   21.0 KB
-    __shared__ __align__(16) uint16_t s_patch[ST_PR * ST_PITCH];     //            4.6 KB
-    __shared__ __align__(16) uint16_t s_out[ST_TH * ST_TW * ST_CO];  // [pix][co] 16.0 KB
-    __shared__ int16_t s_koff[ST_KP];
+    __shared__ __align__(16) uint16_t s_w[ST_CO * ST_WFPITCH];       // [co][kh*24 + kw*3+ci]  23.0 KB
+    __shared__ __align__(16) uint16_t s_patch[ST_PR * ST_PITCH + 8]; //                          4.6 KB
+    __shared__ __align__(16) uint16_t s_out[ST_TH * ST_TW * ST_CO];  // [pix][co]               16.0 KB
+    __shared__ int16_t s_koff[ST_KF];                                // even k -> patch offset
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
 
-    for (int e = tid; e < ST_CO * ST_WPITCH; e += ST_THREADS) {
-        const int co = e / ST_WPITCH, k = e - co * ST_WPITCH;
-        s_w[e] = (k < ST_K) ? w[co * ST_K + k] : (uint16_t)0;
+    for (int e = tid; e < ST_CO * ST_WFPITCH; e += ST_THREADS) {
+        const int co = e / ST_WFPITCH, k = e - co * ST_WFPITCH;
+        const int kh = k / 24, r = k - kh * 24;
+        s_w[e] = (kh < 7 && r < 21) ? w[co * ST_K + kh * 21 + r] : (uint16_t)0;   // pads are ZERO
     }
-    fill_koff(s_koff);
+    for (int k = tid; k < ST_KF; k += ST_THREADS)       // padded taps read finite neighbours (x 0)
+        s_koff[k] = (k < 168) ? (int16_t)((k / 24) * ST_PITCH + (k % 24)) : (int16_t)0;
+    if (tid < 8) s_patch[ST_PR * ST_PITCH + tid] = 0;
 
     const int tiles_w = (OW + ST_TW - 1) / ST_TW, tiles_h = (OH + ST_TH - 1) / ST_TH;
     const long long n_tiles = (long long)N * tiles_h * tiles_w;
@@ -104,20 +112,20 @@ stem_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
         float acc[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-        const int base0 = (2 * warp) * ST_PITCH + 6 * gid;
-        const int base1 = base0 + 6 * 8;
+        const uint16_t* p0 = s_patch + (2 * warp) * ST_PITCH + 6 * gid;      // even offsets only
+        const uint16_t* p1 = p0 + 6 * 8;
 #pragma unroll 2
-        for (int ks = 0; ks < ST_KP / 16; ++ks) {
+        for (int ks = 0; ks < ST_KF / 16; ++ks) {
             const int k0 = ks * 16 + tig * 2;
-            const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o2 = s_koff[k0 + 8], o3 = s_koff[k0 + 9];
+            const int o0 = s_koff[k0], o2 = s_koff[k0 + 8];
             uint32_t a[4];
-            a[0] = pack2(o0 >= 0 ? s_patch[base0 + o0] : 0, o1 >= 0 ? s_patch[base0 + o1] : 0);
-            a[1] = pack2(o0 >= 0 ? s_patch[base1 + o0] : 0, o1 >= 0 ? s_patch[base1 + o1] : 0);
-            a[2] = pack2(o2 >= 0 ? s_patch[base0 + o2] : 0, o3 >= 0 ? s_patch[base0 + o3] : 0);
-            a[3] = pack2(o2 >= 0 ? s_patch[base1 + o2] : 0, o3 >= 0 ? s_patch[base1 + o3] : 0);
+            a[0] = *reinterpret_cast<const uint32_t*>(p0 + o0);
+            a[1] = *reinterpret_cast<const uint32_t*>(p1 + o0);
+            a[2] = *reinterpret_cast<const uint32_t*>(p0 + o2);
+            a[3] = *reinterpret_cast<const uint32_t*>(p1 + o2);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint16_t* wr = s_w + (j * 8 + gid) * ST_WPITCH + k0;
+                const uint16_t* wr = s_w + (j * 8 + gid) * ST_WFPITCH + k0;
                 uint32_t b[2];
                 b[0] = *reinterpret_cast<const uint32_t*>(wr);
                 b[1] = *reinterpret_cast<const uint32_t*>(wr + 8);
@@ -154,7 +162,7 @@ stem_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
 // ---------------------------------------------------------------------------
 // weight gradient: dw_acc[co][k] (fp32, zero-initialised) += sum over pixels
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(ST_THREADS, 1)
+__global__ void __launch_bounds__(ST_THREADS, 2)
 stem_wgrad_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
                   float* __restrict__ dw_acc, int N, int H, int W, int OH, int OW)
 {
@@ -254,7 +262,7 @@ cudaError_t stem_launch_wgrad(const void* x, const void* dy, float* dw_acc, int 
                               int OH, int OW, cudaStream_t st)
 {
     const long long tiles = (long long)N * ((OH + ST_TH - 1) / ST_TH) * ((OW + ST_TW - 1) / ST_TW);
-    int grid = 148;
+    int grid = 148 * 2;
     if (tiles < grid) grid = (int)tiles;
     stem_wgrad_kernel<<<grid, ST_THREADS, 0, st>>>((const uint16_t*)x, (const uint16_t*)dy, dw_acc,
                                                    N, H, W, OH, OW);
