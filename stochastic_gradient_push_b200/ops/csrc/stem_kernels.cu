@@ -55,18 +55,44 @@ __device__ __forceinline__ void fill_koff(int16_t* koff) {
         koff[k] = (k < ST_K) ? (int16_t)((k / 21) * ST_PITCH + (k % 21)) : (int16_t)-1;
 }
 
-// copy the input window of tile (n, oh0, ow0) into smem, zero outside the image
-__device__ __forceinline__ void load_patch(uint16_t* patch, const uint16_t* __restrict__ x,
-                                           int n, int oh0, int ow0, int H, int W)
+// The input window of a tile is fetched in two halves so that global-memory latency hides
+// behind the previous tile's math: `patch_fetch` issues the loads into registers (one tile
+// AHEAD), `patch_commit` writes them to shared memory once the current tile is done.
+#define ST_PATCH_ELEMS (ST_PR * ST_PITCH)                                  // 2352
+#define ST_PATCH_PER_THREAD ((ST_PATCH_ELEMS + ST_THREADS - 1) / ST_THREADS)   // 10
+
+struct TileCoord { int n, oh0, ow0; };
+
+__device__ __forceinline__ TileCoord tile_coord(long long t, int tiles_h, int tiles_w) {
+    TileCoord c;
+    c.ow0 = (int)(t % tiles_w) * ST_TW;
+    c.oh0 = (int)((t / tiles_w) % tiles_h) * ST_TH;
+    c.n = (int)(t / ((long long)tiles_w * tiles_h));
+    return c;
+}
+
+__device__ __forceinline__ void patch_fetch(uint16_t (&reg)[ST_PATCH_PER_THREAD],
+                                            const uint16_t* __restrict__ x, TileCoord tc, int H, int W)
 {
-    const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
-    for (int e = threadIdx.x; e < ST_PR * ST_PITCH; e += ST_THREADS) {
+    const int ih0 = 2 * tc.oh0 - 3, iw0 = 2 * tc.ow0 - 3;
+#pragma unroll
+    for (int i = 0; i < ST_PATCH_PER_THREAD; ++i) {
+        const int e = threadIdx.x + i * ST_THREADS;
         const int r = e / ST_PITCH, c = e - r * ST_PITCH;       // c = col*3 + ci
         const int ih = ih0 + r, iw = iw0 + c / 3;
         uint16_t v = 0;
-        if (c < ST_PC * 3 && ih >= 0 && ih < H && iw >= 0 && iw < W)
-            v = x[((size_t)(n * H + ih) * W + iw) * 3 + (c % 3)];
-        patch[e] = v;
+        if (e < ST_PATCH_ELEMS && c < ST_PC * 3 && ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = x[((size_t)(tc.n * H + ih) * W + iw) * 3 + (c % 3)];
+        reg[i] = v;
+    }
+}
+
+__device__ __forceinline__ void patch_commit(uint16_t* patch, const uint16_t (&reg)[ST_PATCH_PER_THREAD])
+{
+#pragma unroll
+    for (int i = 0; i < ST_PATCH_PER_THREAD; ++i) {
+        const int e = threadIdx.x + i * ST_THREADS;
+        if (e < ST_PATCH_ELEMS) patch[e] = reg[i];
     }
 }
 
@@ -99,14 +125,17 @@ stem_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
     const int tiles_w = (OW + ST_TW - 1) / ST_TW, tiles_h = (OH + ST_TH - 1) / ST_TH;
     const long long n_tiles = (long long)N * tiles_h * tiles_w;
 
+    uint16_t pre[ST_PATCH_PER_THREAD];
+    if ((long long)blockIdx.x < n_tiles) patch_fetch(pre, x, tile_coord(blockIdx.x, tiles_h, tiles_w), H, W);
+
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int tw = (int)(t % tiles_w);
-        const int th = (int)((t / tiles_w) % tiles_h);
-        const int n = (int)(t / ((long long)tiles_w * tiles_h));
-        const int oh0 = th * ST_TH, ow0 = tw * ST_TW;
+        const TileCoord tc = tile_coord(t, tiles_h, tiles_w);
+        const int n = tc.n, oh0 = tc.oh0, ow0 = tc.ow0;
         __syncthreads();                      // previous tile's smem fully consumed
-        load_patch(s_patch, x, n, oh0, ow0, H, W);
+        patch_commit(s_patch, pre);
         __syncthreads();
+        if (t + gridDim.x < n_tiles)          // next tile's loads fly during this tile's math
+            patch_fetch(pre, x, tile_coord(t + gridDim.x, tiles_h, tiles_w), H, W);
 
         // warp `warp` owns output row pr = warp: pixels (pr, pc = gid) and (pr, gid + 8)
         float acc[8][4];
@@ -184,25 +213,45 @@ stem_wgrad_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ d
     const int tiles_w = (OW + ST_TW - 1) / ST_TW, tiles_h = (OH + ST_TH - 1) / ST_TH;
     const long long n_tiles = (long long)N * tiles_h * tiles_w;
 
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int tw = (int)(t % tiles_w);
-        const int th = (int)((t / tiles_w) % tiles_h);
-        const int n = (int)(t / ((long long)tiles_w * tiles_h));
-        const int oh0 = th * ST_TH, ow0 = tw * ST_TW;
-        __syncthreads();
-        load_patch(s_patch, x, n, oh0, ow0, H, W);
-        // dy tile, transposed to [co][pixel] so two consecutive pixels share a 32-bit word
-        for (int e = tid; e < ST_TH * ST_TW * (ST_CO / 8); e += ST_THREADS) {
-            const int p = e >> 3, part = e & 7;
-            const int oh = oh0 + p / ST_TW, ow = ow0 + p % ST_TW;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (oh < OH && ow < OW)
-                v = *reinterpret_cast<const uint4*>(dy + (((size_t)n * OH + oh) * OW + ow) * ST_CO + part * 8);
-            const uint16_t* h = reinterpret_cast<const uint16_t*>(&v);
+    // register prefetch of the NEXT tile (input patch + the 4 x 16 B of dy this thread stages)
+    uint16_t pre[ST_PATCH_PER_THREAD];
+    uint4 dpre[4];
+    auto dy_fetch = [&](TileCoord tc) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s_dyT[(part * 8 + i) * DP + p] = h[i];
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * ST_THREADS;
+            const int p = e >> 3, part = e & 7;
+            const int oh = tc.oh0 + p / ST_TW, ow = tc.ow0 + p % ST_TW;
+            dpre[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (oh < OH && ow < OW)
+                dpre[i] = *reinterpret_cast<const uint4*>(
+                    dy + (((size_t)tc.n * OH + oh) * OW + ow) * ST_CO + part * 8);
+        }
+    };
+    if ((long long)blockIdx.x < n_tiles) {
+        const TileCoord tc0 = tile_coord(blockIdx.x, tiles_h, tiles_w);
+        patch_fetch(pre, x, tc0, H, W);
+        dy_fetch(tc0);
+    }
+
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        __syncthreads();
+        patch_commit(s_patch, pre);
+        // dy tile, transposed to [co][pixel] so two consecutive pixels share a 32-bit word
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * ST_THREADS;
+            const int p = e >> 3, part = e & 7;
+            const uint16_t* h = reinterpret_cast<const uint16_t*>(&dpre[i]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s_dyT[(part * 8 + q) * DP + p] = h[q];
         }
         __syncthreads();
+        if (t + gridDim.x < n_tiles) {
+            const TileCoord tn = tile_coord(t + gridDim.x, tiles_h, tiles_w);
+            patch_fetch(pre, x, tn, H, W);
+            dy_fetch(tn);
+        }
 
         // GEMM K dimension = the tile's 128 pixels, 16 per step (one output row per step)
 #pragma unroll 1
