@@ -43,7 +43,7 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
             for (int kw = 0; kw < k; ++kw) {
                 const int iw = w0 + kw;
                 if (iw < 0 || iw >= W) continue;
-                const F8 v = Io<T>::load(x + (((long long)n * H + ih) * W + iw) * C + cv * 8);
+                const F8 v = Io<T>::load_cached(x + (((long long)n * H + ih) * W + iw) * C + cv * 8);
                 const int c = kh * k + kw;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -87,8 +87,8 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ code, T
                 const int kw = iw + p - ow * s;
                 const uint32_t mine = (uint32_t)(kh * k + kw);
                 const long long o = (((long long)n * OH + oh) * OW + ow) * C + cv * 8;
-                const uint2 cd = *reinterpret_cast<const uint2*>(code + o);
-                const F8 g = Io<T>::load(dy + o);
+                const uint2 cd = __ldg(reinterpret_cast<const uint2*>(code + o));
+                const F8 g = Io<T>::load_cached(dy + o);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (((cd.x >> (8 * i)) & 0xffu) == mine) acc.v[i] += g.v[i];

@@ -21,6 +21,11 @@ template <> struct Io<__nv_bfloat16> {
         return r;
     }
     static __device__ __forceinline__ F8 load(const __nv_bfloat16* p) { return decode(load_raw(p)); }
+    // read-only path WITH L1 allocation: for data that neighbouring threads re-read
+    // (pooling windows overlap); the streaming loads above bypass L1 on purpose
+    static __device__ __forceinline__ F8 load_cached(const __nv_bfloat16* p) {
+        return decode(__ldg(reinterpret_cast<const uint4*>(p)));
+    }
     static __device__ __forceinline__ F8 decode(const raw_t& r) {
         F8 o;
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -46,6 +51,14 @@ template <> struct Io<__nv_bfloat16> {
 template <> struct Io<float> {
     typedef F8 raw_t;
     static __device__ __forceinline__ raw_t load_raw(const float* p) { return load(p); }
+    static __device__ __forceinline__ F8 load_cached(const float* p) {
+        F8 o;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w;
+        o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+        return o;
+    }
     static __device__ __forceinline__ F8 decode(const raw_t& r) { return r; }
     static __device__ __forceinline__ F8 load(const float* p) {
         F8 o;
