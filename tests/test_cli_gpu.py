@@ -20,8 +20,7 @@ def _torchrun(nproc, script, args, port, timeout=600):
 
 COMMON = ['--model', 'tiny', '--num_classes', '10', '--image_size', '32', '--synthetic', 'True',
           '--synthetic_len', '256', '--batch_size', '16', '--verbose', 'False', '--print_freq', '2',
-          '--num_dataloader_workers', '0', '--lr', '0.05', '--num_epochs', '2',
-          '--num_itr_ignore', '0']
+          '--num_dataloader_workers', '0', '--lr', '0.05', '--num_epochs', '2']
 
 
 @pytest.mark.parametrize('extra', [
@@ -32,8 +31,8 @@ COMMON = ['--model', 'tiny', '--num_classes', '10', '--image_size', '32', '--syn
     ['--all_reduce', 'True', '--graph_type', '-1'],
 ])
 def test_gossip_sgd_cli_on_gpus(tmp_path, master_port, extra):
-    out = _torchrun(2, 'gossip_sgd.py', COMMON + extra + ['--checkpoint_dir', str(tmp_path) + '/'],
-                    master_port)
+    out = _torchrun(2, 'gossip_sgd.py', COMMON + extra + [
+        '--checkpoint_dir', str(tmp_path) + '/', '--num_itr_ignore', '0'], master_port)
     assert out.returncode == 0, out.stdout[-3000:]
     if '--all_reduce' not in extra:
         assert 'transport: nvlink' in out.stdout
