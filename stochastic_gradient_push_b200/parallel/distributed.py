@@ -312,6 +312,12 @@ class GossipDataParallel(Module):
         # -- data plane ------------------------------------------------------- #
         self._kernel = None
         self._c10d = None
+        # hierarchical mode: the node masters rendezvous among themselves; new_group is
+        # collective over the WHOLE world, so every rank creates it
+        self._masters_group = None
+        if self.nprocs_per_node > 1 and use_kernels and world_size > 1 and dist.is_initialized():
+            self._masters_group = dist.new_group(
+                [r * self.nprocs_per_node for r in range(world_size)])
         if self.is_local_master:
             if use_kernels:
                 if symmetric_world is None:
@@ -370,11 +376,7 @@ class GossipDataParallel(Module):
         from .symmetric import LocalWorld, SymmetricWorld
         if world_size == 1:
             return LocalWorld(1, [device.index]).view(0)
-        group = None
-        if self.nprocs_per_node > 1:
-            masters = [r * self.nprocs_per_node for r in range(world_size)]
-            group = dist.new_group(masters)
-        return SymmetricWorld(device, group)
+        return SymmetricWorld(device, self._masters_group)
 
     # ------------------------------------------------------------------ #
     # properties
