@@ -1,0 +1,94 @@
+"""Per-layer A/B of the ResNet-50 1x1 convolutions (forward, training mode):
+
+    library conv  + fused-BN (stats pass + finalize + apply)      <- default path
+    tcgen05 GEMM with the statistics in its epilogue + finalize + apply
+
+CUDA-event timing, L2 flushed between iterations, median of ``--iters`` runs.
+
+    python benchmarks/conv1x1_bench.py --batch 256 --out gpurun_out/conv1x1_bench.json
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from stochastic_gradient_push_b200.ops import fused_bn, native          # noqa: E402
+from stochastic_gradient_push_b200.ops.fused_bn import FusedBatchNormAct2d, conv_bn_act   # noqa: E402
+
+# (H=W, C_in, C_out, residual) of every stride-1 1x1 convolution in ResNet-50, with multiplicity
+LAYERS = [
+    (56, 64, 64, False, 1), (56, 64, 256, False, 1), (56, 64, 256, True, 3), (56, 256, 64, False, 2),
+    (56, 256, 128, False, 1), (28, 128, 512, True, 4), (28, 512, 128, False, 3),
+    (28, 512, 256, False, 1), (14, 256, 1024, True, 6), (14, 1024, 256, False, 5),
+    (14, 1024, 512, False, 1), (7, 512, 2048, True, 3), (7, 2048, 512, False, 2),
+]
+
+
+def timed(fn, iters, flush):
+    ts = []
+    for _ in range(iters):
+        flush.add_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--iters', type=int, default=15)
+    ap.add_argument('--out', default='')
+    args = ap.parse_args()
+    native.load()
+    flush = torch.zeros(64 * 1024 * 1024, device='cuda')          # 256 MB > L2
+    rows, tot_lib, tot_tc = [], 0.0, 0.0
+    for hw, cin, cout, add, mult in LAYERS:
+        conv = nn.Conv2d(cin, cout, 1, bias=False).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        bn = FusedBatchNormAct2d(cout).cuda()
+        x = torch.randn(args.batch, cin, hw, hw, device='cuda').to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        res = torch.randn(args.batch, cout, hw, hw, device='cuda').to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last) if add else None
+        w = conv.weight.detach()
+        C = native.load()
+        out = {}
+        with torch.no_grad():
+            for name, use in (('library', False), ('tcgen05', True)):
+                fused_bn.USE_TCGEN05_CONV1X1 = use
+                fn = lambda: conv_bn_act(conv, bn, x, residual=res, relu=True)   # noqa: E731
+                for _ in range(3):
+                    fn()
+                out[name] = timed(fn, args.iters, flush)
+            out['lib_conv_only'] = timed(lambda: conv(x), args.iters, flush)
+            out['tc_gemm_only'] = timed(lambda: C.conv1x1_forward(x, w), args.iters, flush)
+        M = args.batch * hw * hw
+        gemm_bytes = 2.0 * (M * cin + M * cout + cin * cout)
+        rows.append(dict(hw=hw, cin=cin, cout=cout, add=add, mult=mult, M=M,
+                         gemm_tbps=gemm_bytes / out['tc_gemm_only'] / 1e9,
+                         lib_conv_tbps=gemm_bytes / out['lib_conv_only'] / 1e9, **out))
+        tot_lib += mult * out['library']
+        tot_tc += mult * out['tcgen05']
+        print('%3dx%-3d %4d->%-4d add=%d x%d | conv+bn: lib %.3f ms  tcgen05 %.3f ms | conv only: lib %.3f '
+              '(%.2f TB/s)  tcgen05 %.3f (%.2f TB/s)' % (
+                  hw, hw, cin, cout, add, mult, out['library'], out['tcgen05'], out['lib_conv_only'],
+                  rows[-1]['lib_conv_tbps'], out['tc_gemm_only'], rows[-1]['gemm_tbps']), flush=True)
+    print('ResNet-50 fwd 1x1 conv+BN total: library %.3f ms, tcgen05 %.3f ms' % (tot_lib, tot_tc))
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
+        with open(args.out, 'w') as f:
+            json.dump(dict(batch=args.batch, total_library_ms=tot_lib, total_tcgen05_ms=tot_tc, layers=rows), f,
+                      indent=1)
+
+
+if __name__ == '__main__':
+    main()

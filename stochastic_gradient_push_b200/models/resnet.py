@@ -24,7 +24,7 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
-from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC, stem_conv
+from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC, conv_bn_act, stem_conv
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -52,7 +52,7 @@ class BasicBlock(nn.Module):
         return self.bn2
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
+        identity = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
         out = self.bn1(self.conv1(x), relu=True)
         return self.bn2(self.conv2(out), residual=identity, relu=True)
 
@@ -76,10 +76,10 @@ class Bottleneck(nn.Module):
         return self.bn3
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
-        out = self.bn1(self.conv1(x), relu=True)
+        identity = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
+        out = conv_bn_act(self.conv1, self.bn1, x, relu=True)
         out = self.bn2(self.conv2(out), relu=True)
-        return self.bn3(self.conv3(out), residual=identity, relu=True)
+        return conv_bn_act(self.conv3, self.bn3, out, residual=identity, relu=True)
 
 
 class ResNet(nn.Module):

@@ -248,8 +248,107 @@ static torch::Tensor stem_wgrad(torch::Tensor x, torch::Tensor dy)
     return acc.permute({0, 3, 1, 2});
 }
 
+// ---------------------------------------------------------------------------
+// 1x1 convolution as a tcgen05 GEMM, BatchNorm statistics fused into its epilogue
+// (conv1x1_kernels.cu)
+// ---------------------------------------------------------------------------
+extern "C" {
+int c1_supported(long long M, int N, int K);
+int c1_partial_rows(long long M, int N, int num_sms);
+cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
+                           int num_sms, cudaStream_t st);
+cudaError_t c1_launch_stats_finalize(const float* partial, int R, int C, const float* gamma, const float* beta,
+                                     float* rmean, float* rvar, long long* nbt, float momentum, float eps,
+                                     float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
+}
+
+// x: NHWC bf16 activation (4-D channels_last) or [M, K] matrix; w: [N, K, 1, 1] or [N, K], rows contiguous
+static bool conv1x1_can_fuse(const torch::Tensor& x, const torch::Tensor& w)
+{
+    if (!x.is_cuda() || !w.is_cuda() || x.scalar_type() != torch::kBFloat16 || w.scalar_type() != torch::kBFloat16)
+        return false;
+    if (x.dim() == 4) { if (!x.is_contiguous(at::MemoryFormat::ChannelsLast)) return false; }
+    else if (!(x.dim() == 2 && x.is_contiguous())) return false;
+    if (w.dim() == 4) { if (w.size(2) != 1 || w.size(3) != 1) return false; }
+    else if (w.dim() != 2) return false;
+    const int K = (int)x.size(1), N = (int)w.size(0);
+    if (w.size(1) != K || w.stride(1) != 1 || w.stride(0) != K) return false;
+    if ((reinterpret_cast<uintptr_t>(x.data_ptr()) | reinterpret_cast<uintptr_t>(w.data_ptr())) & 15) return false;
+    return c1_supported(x.numel() / K, N, K) != 0;
+}
+
+static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
+{
+    if (x.dim() == 4)
+        return torch::empty({x.size(0), N, x.size(2), x.size(3)},
+                            x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    return torch::empty({x.size(0), N}, x.options());
+}
+
+static int sm_count() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
+
+static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w)
+{
+    TORCH_CHECK(conv1x1_can_fuse(x, w), "conv1x1_forward: unsupported tensors");
+    const int K = (int)x.size(1), N = (int)w.size(0);
+    const long long M = x.numel() / K;
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto y = conv1x1_alloc_out(x, N);
+    BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K, nullptr, sm_count(),
+                            at::cuda::getCurrentCUDAStream()));
+    return y;
+}
+
+// training-mode  out = act(bn(conv1x1(x, w)) [+ residual]);  returns (conv output, out, coef)
+static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Tensor w,
+                                                     c10::optional<torch::Tensor> residual,
+                                                     torch::Tensor gamma, torch::Tensor beta,
+                                                     c10::optional<torch::Tensor> running_mean,
+                                                     c10::optional<torch::Tensor> running_var,
+                                                     c10::optional<torch::Tensor> num_batches_tracked,
+                                                     double momentum, double eps, bool relu)
+{
+    TORCH_CHECK(conv1x1_can_fuse(x, w), "conv1x1_bn_forward: unsupported tensors");
+    const int K = (int)x.size(1), N = (int)w.size(0);
+    const long long M = x.numel() / K;
+    TORCH_CHECK(bn_supported(M, N), "unsupported channel count ", N);
+    TORCH_CHECK(gamma.scalar_type() == torch::kFloat32 && beta.scalar_type() == torch::kFloat32);
+    c10::cuda::CUDAGuard guard(x.get_device());
+    auto st = at::cuda::getCurrentCUDAStream();
+    auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(x.device());
+    auto yraw = conv1x1_alloc_out(x, N);
+    const bool has_res = residual.has_value() && residual->defined();
+    if (has_res) TORCH_CHECK(residual->sizes() == yraw.sizes() && residual->scalar_type() == yraw.scalar_type()
+                             && residual->strides() == yraw.strides());
+    const int sms = sm_count();
+    const int R = c1_partial_rows(M, N, sms);
+    auto partial = torch::empty({R, 4, N}, fopt);
+    BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), yraw.data_ptr(), M, N, K, partial.data_ptr<float>(),
+                            sms, st));
+    auto coef = torch::empty({4, N}, fopt);      // mean, invstd, scale, shift
+    float* mean = coef.data_ptr<float>();
+    float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
+    if (running_mean.has_value() && running_mean->defined()) {
+        rm = running_mean->data_ptr<float>();
+        rv = running_var->data_ptr<float>();
+    }
+    if (num_batches_tracked.has_value() && num_batches_tracked->defined())
+        nbt = reinterpret_cast<long long*>(num_batches_tracked->data_ptr<int64_t>());
+    BN_CHECK(c1_launch_stats_finalize(partial.data_ptr<float>(), R, N, gamma.data_ptr<float>(),
+                                      beta.data_ptr<float>(), rm, rv, nbt, (float)momentum, (float)eps,
+                                      mean, mean + N, mean + 2 * N, mean + 3 * N, st));
+    auto out = torch::empty_like(yraw);
+    BN_CHECK(bn_launch_apply(0, relu ? 1 : 0, has_res ? 1 : 0, yraw.data_ptr(),
+                             has_res ? residual->data_ptr() : nullptr, mean + 2 * N, mean + 3 * N,
+                             out.data_ptr(), M, N, st));
+    return {yraw, out, coef};
+}
+
 void bind_bn(py::module& mod)
 {
+    mod.def("conv1x1_can_fuse", &conv1x1_can_fuse);
+    mod.def("conv1x1_forward", &conv1x1_forward);
+    mod.def("conv1x1_bn_forward", &conv1x1_bn_forward);
     mod.def("stem_can_fuse", &stem_can_fuse);
     mod.def("stem_forward", &stem_forward);
     mod.def("stem_wgrad", &stem_wgrad);

@@ -20,6 +20,8 @@ also the oracle in the numerics tests.
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -28,6 +30,11 @@ from . import native
 
 
 FORCE_REFERENCE = False      # debugging / A-B switch: route everything to the PyTorch composition
+
+# 1x1 convolutions feeding a training-mode BatchNorm run as the tcgen05 GEMM with the
+# statistics fused into its epilogue (csrc/conv1x1_kernels.cu).  SGP_B200_CONV1X1=0 routes
+# them back to the library convolution + stand-alone statistics pass.
+USE_TCGEN05_CONV1X1 = os.environ.get('SGP_B200_CONV1X1', '0') != '0'
 
 
 def _can_fuse(x: torch.Tensor) -> bool:
@@ -109,6 +116,67 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
             self.running_var if self.track_running_stats else None,
             self.num_batches_tracked if (self.track_running_stats and training) else None,
             residual=residual, relu=relu, training=training, momentum=momentum, eps=self.eps)
+
+
+# --------------------------------------------------------------------------- #
+# 1x1 convolution + BatchNorm (+ residual) (+ ReLU)
+# --------------------------------------------------------------------------- #
+class _Conv1x1BNAct(torch.autograd.Function):
+    """``act(bn(conv1x1(x, w)) [+ residual])`` in training mode.  Forward: tcgen05 GEMM
+    whose epilogue also produces the BatchNorm statistics, finalize, apply.  Backward: the
+    fused BN backward, then the library's dgrad / wgrad for the convolution."""
+
+    @staticmethod
+    def forward(ctx, x, w, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu):
+        C = native.load()
+        w16 = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        yraw, out, coef = C.conv1x1_bn_forward(x, w16, residual, gamma, beta, running_mean, running_var,
+                                               nbt, momentum, eps, relu)
+        ctx.relu = relu
+        ctx.add = residual is not None
+        ctx.w_dtype = w.dtype
+        if ctx.add:
+            ctx.save_for_backward(x, w16, yraw, coef, out)
+        else:
+            ctx.save_for_backward(x, w16, yraw, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        C = native.load()
+        x, w16, yraw, coef = ctx.saved_tensors[:4]
+        out = ctx.saved_tensors[4] if ctx.add else None
+        dyraw, dz, ggamma, gbeta = C.bn_backward(dy, yraw, out, coef, ctx.relu, ctx.add)
+        dx, dw, _ = torch.ops.aten.convolution_backward(
+            dyraw, x, w16, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        if dw is not None and dw.dtype != ctx.w_dtype:
+            dw = dw.to(ctx.w_dtype)
+        return dx, dw, (dz if ctx.add else None), ggamma, gbeta, None, None, None, None, None, None
+
+
+def conv_bn_act(conv: nn.Conv2d, bn: 'FusedBatchNormAct2d', x, residual=None, relu=False):
+    """``bn(conv(x), residual=residual, relu=relu)``; 1x1 / stride-1 convolutions of NHWC bf16
+    activations in training mode take the fused tcgen05 path."""
+    if (USE_TCGEN05_CONV1X1 and not FORCE_REFERENCE and bn.training and bn.track_running_stats
+            and x.is_cuda and native.available() and x.dim() == 4
+            and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+            and conv.groups == 1 and conv.bias is None and bn.weight is not None
+            and bn.weight.dtype == torch.float32 and (residual is None or relu)):
+        w = conv.weight
+        if x.dtype == torch.float32 and torch.is_autocast_enabled():
+            x = x.to(torch.bfloat16)
+        if x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last) \
+                and (w.dtype == torch.bfloat16 or torch.is_autocast_enabled()) \
+                and (residual is None or (residual.dtype == torch.bfloat16
+                                          and residual.is_contiguous(memory_format=torch.channels_last))):
+            C = native.load()
+            wk = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+            if C.conv1x1_can_fuse(x, wk) and conv.out_channels % 8 == 0:
+                momentum = 0.1 if bn.momentum is None else bn.momentum
+                return _Conv1x1BNAct.apply(x, w, residual, bn.weight, bn.bias, bn.running_mean,
+                                           bn.running_var, bn.num_batches_tracked, momentum, bn.eps, relu)
+    return bn(conv(x), residual=residual, relu=relu)
 
 
 # --------------------------------------------------------------------------- #
