@@ -71,6 +71,7 @@ def main():
                 out[name] = timed(fn, args.iters, flush)
             out['lib_conv_only'] = timed(lambda: conv(x), args.iters, flush)
             out['tc_gemm_only'] = timed(lambda: C.conv1x1_forward(x, w), args.iters, flush)
+            out['tc_gemm_stats'] = timed(lambda: C.conv1x1_forward(x, w, True), args.iters, flush)
         M = args.batch * hw * hw
         gemm_bytes = 2.0 * (M * cin + M * cout + cin * cout)
         rows.append(dict(hw=hw, cin=cin, cout=cout, add=add, mult=mult, M=M,
@@ -79,9 +80,9 @@ def main():
         tot_lib += mult * out['library']
         tot_tc += mult * out['tcgen05']
         print('%3dx%-3d %4d->%-4d add=%d x%d | conv+bn: lib %.3f ms  tcgen05 %.3f ms | conv only: lib %.3f '
-              '(%.2f TB/s)  tcgen05 %.3f (%.2f TB/s)' % (
+              '(%.2f TB/s)  tcgen05 %.3f (%.2f TB/s), +stats %.3f' % (
                   hw, hw, cin, cout, add, mult, out['library'], out['tcgen05'], out['lib_conv_only'],
-                  rows[-1]['lib_conv_tbps'], out['tc_gemm_only'], rows[-1]['gemm_tbps']), flush=True)
+                  rows[-1]['lib_conv_tbps'], out['tc_gemm_only'], rows[-1]['gemm_tbps'], out['tc_gemm_stats']), flush=True)
     print('ResNet-50 fwd 1x1 conv+BN total: library %.3f ms, tcgen05 %.3f ms' % (tot_lib, tot_tc))
     if args.out:
         os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)

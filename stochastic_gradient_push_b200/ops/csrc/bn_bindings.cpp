@@ -287,14 +287,20 @@ static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
 
 static int sm_count() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
 
-static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w)
+// with_stats: also run the statistics epilogue into a scratch buffer (benchmarking the GEMM alone)
+static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w, bool with_stats)
 {
     TORCH_CHECK(conv1x1_can_fuse(x, w), "conv1x1_forward: unsupported tensors");
     const int K = (int)x.size(1), N = (int)w.size(0);
     const long long M = x.numel() / K;
     c10::cuda::CUDAGuard guard(x.get_device());
     auto y = conv1x1_alloc_out(x, N);
-    BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K, nullptr, sm_count(),
+    torch::Tensor partial;
+    if (with_stats)
+        partial = torch::empty({c1_partial_rows(M, N, sm_count()), 3, N},
+                               torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
+    BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K,
+                            with_stats ? partial.data_ptr<float>() : nullptr, sm_count(),
                             at::cuda::getCurrentCUDAStream()));
     return y;
 }
@@ -322,7 +328,7 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
                              && residual->strides() == yraw.strides());
     const int sms = sm_count();
     const int R = c1_partial_rows(M, N, sms);
-    auto partial = torch::empty({R, 4, N}, fopt);
+    auto partial = torch::empty({R, 3, N}, fopt);
     BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), yraw.data_ptr(), M, N, K, partial.data_ptr<float>(),
                             sms, st));
     auto coef = torch::empty({4, N}, fopt);      // mean, invstd, scale, shift
@@ -347,7 +353,7 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
 void bind_bn(py::module& mod)
 {
     mod.def("conv1x1_can_fuse", &conv1x1_can_fuse);
-    mod.def("conv1x1_forward", &conv1x1_forward);
+    mod.def("conv1x1_forward", &conv1x1_forward, py::arg("x"), py::arg("w"), py::arg("with_stats") = false);
     mod.def("conv1x1_bn_forward", &conv1x1_bn_forward);
     mod.def("stem_can_fuse", &stem_can_fuse);
     mod.def("stem_forward", &stem_forward);

@@ -9,23 +9,31 @@
 // GEMMs are HBM-bound (K is 64..2048 and M is up to 802,816), so the kernel is
 // organised around the epilogue, not the MMA:
 //
-//   warp 0   TMA producer   X / W tiles -> 128B-swizzled smem ring (cp.async.bulk.tensor,
-//                           mbarrier complete_tx); X is streamed evict_first, W evict_last
+//   warp 0   TMA producer   X tiles -> 128B-swizzled smem ring (cp.async.bulk.tensor, mbarrier
+//                           complete_tx).  The CTA's W block [BN, K] is loaded ONCE and stays
+//                           resident whenever it fits next to a >= 3-deep X ring (K*BN <= 64K
+//                           elements); otherwise W tiles travel through the ring with X.
 //   warp 1   MMA issuer     one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16,
 //                           accumulators in TMEM, double-buffered (2 x BN columns) so the
 //                           MMAs of tile i+1 run under the epilogue of tile i
-//   warp 2-5 epilogue       tcgen05.ld (32 lanes x 32 columns) -> bf16 -> swizzled smem ->
-//                           TMA store; then every thread owns a pair of channels of the
-//                           staged tile and accumulates n / shifted sum / shifted sum of
-//                           squares of the ROUNDED outputs (what BatchNorm will read)
+//   warp 2-9 epilogue       two sets of four warps, set h drains accumulator stage h (every other
+//                           tile).  Each warp owns 32 tile rows (its TMEM lane quadrant) end to end:
+//                           tcgen05.ld (32 lanes x 64 columns) -> bf16 -> its own 4 KB swizzled
+//                           slab -> its own TMA store (box 64 x 32), then the statistics of
+//                           exactly those rows are read back from the slab (lane = channel pair):
+//                           n / shifted sum / shifted sum of squares of the ROUNDED outputs
+//                           (what BatchNorm will read).  No CTA-wide barrier in the loop; slabs
+//                           recycle through the issuing lane's bulk-group counter.
 //
 // The grid is persistent: CTA (nb, j) owns output-channel block nb for its whole life
 // and walks the row tiles j, j + ctas_per_n, ...; its statistics therefore stay in
-// registers until the end, when each thread writes one partial row
-// (n, K, sum(y-K), sum((y-K)^2)); c1_stats_finalize_kernel merges the <= 592 partial rows
-// with the pairwise (Chan) update and emits mean / invstd / scale / shift and the
-// running-statistics update, exactly what bn_stats_finalize_kernel does for the
-// stand-alone statistics pass.
+// registers until the end: each epilogue warp keeps (n, K, sum(y-K), sum((y-K)^2)) with its
+// own shift K (its first output row), the eight warps are merged in shared memory into one
+// (n, mean, M2) row per CTA, and c1_stats_finalize_kernel merges the <= 148 rows with the
+// pairwise (Chan) update and emits mean / invstd / scale / shift and the running-statistics update, exactly what
+// bn_stats_finalize_kernel does for the stand-alone statistics pass.
+//
+// Measured on B200 (benchmarks/conv1x1_bench.py, profiles/conv1x1_bench_*.log).
 //
 // Reference call site: torchvision Bottleneck conv1/conv3 + BatchNorm2d inside
 // /root/reference/gossip_sgd.py (models.resnet50()).
@@ -41,20 +49,16 @@ constexpr int BM = 128;                 // rows per tile == TMEM lanes == UMMA_M
 constexpr int BK = 64;                  // bf16 per k-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KB
-constexpr int SUB_BYTES = BM * 128;     // one 64-column output sub-tile, 16 KB
-constexpr int kThreads = 192;           // producer warp, MMA warp, 4 epilogue warps
-constexpr int kEpiThreads = 128;
+constexpr int SLAB_BYTES = 32 * 128;    // one epilogue warp's store slab: 32 rows x 64 bf16, 4 KB
+constexpr int kThreads = 320;           // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+constexpr int SMEM_FIXED = 1024 + 256;  // alignment slack + barriers / TMEM slot
 
+// cute::TMA::CacheHintSm90 encodings
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-
-template <int BN> struct Cfg {
-    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int O_BYTES = (BN / 64) * SUB_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;         // 128 / 256 / 512: powers of two
-    static constexpr int SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + O_BYTES + 256;
-};
 
 // ---------------------------------------------------------------------------
 // PTX helpers
@@ -111,11 +115,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
         "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(tm)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 "r"(src_smem), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
@@ -177,50 +181,63 @@ __device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_f32, uint32_t hi_f32)
     return r;
 }
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-
 // ---------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------
+struct C1Plan {            // host-computed shared-memory plan (bytes are multiples of 1024)
+    int stages;            // depth of the X (or X+W) ring, 2..MAX_STAGES
+    int resident;          // 1: this CTA's whole W block [BN, K] is loaded once and stays in smem
+    int nbuf;              // store slabs per epilogue warp (2 or 1)
+    int x_hint_first;      // 1: X tiles are read by one CTA only -> L2 evict_first
+};
+
 template <int BN, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_y, int M, int N, int K, float* __restrict__ partial)
+               const __grid_constant__ CUtensorMap tm_y, int M, int N, int K, float* __restrict__ partial,
+               const C1Plan plan)
 {
-    using C = Cfg<BN>;
-    constexpr int STAGES = C::STAGES;
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int NS = BN / 64;               // 64-column sub-tiles per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + STAGES * A_BYTES;
-    uint8_t* sO = sB + STAGES * C::B_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sO + C::O_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;        // accumulator stage ready for the epilogue
-    uint64_t* tempty = tfull + 2;            // accumulator stage drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5;       // warp-uniform
+    const int warp = threadIdx.x >> 5;        // warp-uniform
     const int lane = threadIdx.x & 31;
-
     const int n_blocks = N / BN;
     const int ctas_per_n = gridDim.x / n_blocks;
     const int nb = blockIdx.x % n_blocks;
     const int j = blockIdx.x / n_blocks;
     const int m_tiles = (M + BM - 1) / BM;
     const int k_blocks = (K + BK - 1) / BK;
+    const int stages = plan.stages;
+    const bool resident = plan.resident != 0;
+    const int nbuf = plan.nbuf;
+
+    // [ resident W : k_blocks x B_BYTES ][ ring : stages x (X tile [+ W tile]) ][ store slabs ][ barriers ]
+    uint8_t* sW = smem;
+    uint8_t* ring = sW + (resident ? k_blocks * B_BYTES : 0);
+    const int stage_bytes = A_BYTES + (resident ? 0 : B_BYTES);
+    uint8_t* sO = ring + stages * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sO + 8 * nbuf * SLAB_BYTES);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;    // accumulator stage ready for the epilogue
+    uint64_t* tempty = tfull + 2;            // accumulator stage drained
+    uint64_t* wfull = tempty + 2;            // resident W landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_y);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)C::TMEM_COLS)
+                     "r"((uint32_t)(2 * BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -232,15 +249,22 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            if (resident) {
+                mbar_expect_tx(wfull, (uint32_t)(k_blocks * B_BYTES));
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    tma_load_2d(&tm_w, wfull, sW + kb * B_BYTES, kb * BK, nb * BN, L2_EVICT_LAST);
+            }
+            const uint64_t x_hint = plan.x_hint_first ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = j; mt < m_tiles; mt += ctas_per_n) {
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_BYTES + C::B_BYTES);
-                    tma_load_2d(&tm_x, &full[stage], sA + stage * A_BYTES, kb * BK, mt * BM, L2_EVICT_FIRST);
-                    tma_load_2d(&tm_w, &full[stage], sB + stage * C::B_BYTES, kb * BK, nb * BN, L2_EVICT_LAST);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    uint8_t* dst = ring + stage * stage_bytes;
+                    tma_load_2d(&tm_x, &full[stage], dst, kb * BK, mt * BM, x_hint);
+                    if (!resident) tma_load_2d(&tm_w, &full[stage], dst + A_BYTES, kb * BK, nb * BN, L2_EVICT_LAST);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -251,6 +275,7 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                        ((uint32_t)(BM >> 4) << 24);
+            if (resident) { mbar_wait(wfull, 0); tc_fence_after(); }
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -262,14 +287,16 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
-                    const uint64_t b_desc = umma_desc_sw128(smem_u32(sB + stage * C::B_BYTES));
+                    const uint8_t* a_ptr = ring + stage * stage_bytes;
+                    const uint8_t* b_ptr = resident ? sW + kb * B_BYTES : a_ptr + A_BYTES;
+                    const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ptr));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ptr));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per UMMA_K inside the swizzle row
                         umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
                                   (uint32_t)((kb | k) != 0));
                     umma_commit(&empty[stage]);                 // smem slot free once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[as]);
                 as ^= 1;
@@ -278,99 +305,145 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         }
     } else {
         // ===================== epilogue =====================
-        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-        const int et = threadIdx.x - 64;              // 0..127
-        const int row = q * 32 + lane;                // tile row owned for the TMEM -> smem copy
-        constexpr int P = BN / 2;                     // bf16 pairs per tile row
-        constexpr int G = kEpiThreads / P;            // row groups for the statistics (1, 2, 4)
-        constexpr int RG = BM / G;                    // rows per group
-        const int w = et % P;
-        const int rg = et / P;
-        const uint32_t stat_base = smem_u32(sO) + (uint32_t)((w >> 5) * SUB_BYTES + (w & 3) * 4);
-        const int jchunk = (w & 31) >> 2;
-        float cnt = 0.f, k0 = 0.f, k1 = 0.f, s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        // Two sets of four warps; set h drains accumulator stage h, i.e. every other tile, so each
+        // SM sub-partition always has two epilogue warps to interleave (one warp per scheduler
+        // exposes every TMEM / smem latency: ncu showed the statistics loop running at IPC ~0.4).
+        // Within a set, warp q owns tile rows [32q, 32q+32) (its TMEM lane quadrant) end to end:
+        // TMEM -> bf16 -> its own 4 KB swizzled slab -> its own TMA store (box 64 x 32) ->
+        // statistics of exactly those rows read back from the slab.  No CTA-wide barrier; slabs
+        // are recycled through the issuing lane's bulk-group counter.
+        const int set = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const uint32_t slab0 = smem_u32(sO) + (uint32_t)((set * 4 + q) * nbuf * SLAB_BYTES);
+        const uint32_t wr_off = (uint32_t)(lane * 128);                    // this lane's row in the slab
+        const uint32_t rd_off = (uint32_t)((lane & 3) * 4);                // this lane's bf16 pair in a row
+        const int rd_chunk = lane >> 2;
+        int slot = 0;
+        float cnt = 0.f;
+        float k0[NS], k1[NS], s0[NS], s1[NS], q0[NS], q1[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { k0[s] = k1[s] = s0[s] = s1[s] = q0[s] = q1[s] = 0.f; }
         bool have_k = false;
-        int as = 0;
+        const int as = set;
         uint32_t aphase = 0;
-        for (int mt = j; mt < m_tiles; mt += ctas_per_n) {
+        for (int mt = j + set * ctas_per_n; mt < m_tiles; mt += 2 * ctas_per_n) {
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
-            epi_barrier();
+            const int nrows = min(32, M - mt * BM - q * 32);       // rows of this slab that exist (<= 0: none)
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_row + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
-                const uint32_t dst = smem_u32(sO) + (uint32_t)((c >> 1) * SUB_BYTES + row * 128);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t chunk = (uint32_t)(((c & 1) * 4 + i) ^ (row & 7));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + chunk * 16),
+            for (int s = 0; s < NS; ++s) {
+                const uint32_t slab = slab0 + (uint32_t)(slot * SLAB_BYTES);
+                if (lane == 0) {                                   // the store that last used this slab has read it
+                    if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
+                uint32_t v[64];
+                tmem_ld32(t_row + (uint32_t)(s * 64), v);
+                tmem_ld32(t_row + (uint32_t)(s * 64 + 32), v + 32);
+                tmem_ld_wait();
+                if (s == NS - 1) {                                 // accumulator fully read: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t chunk = (uint32_t)(i ^ (lane & 7));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + wr_off + chunk * 16),
                                  "r"(pack_bf16(v[8 * i + 0], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
                                  "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
                                  : "memory");
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);                    // MMA may overwrite this stage
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> TMA reads
-            epi_barrier();
-            if (et == 0) {
-#pragma unroll
-                for (int sub = 0; sub < BN / 64; ++sub)
-                    tma_store_2d(&tm_y, sO + sub * SUB_BYTES, nb * BN + sub * 64, mt * BM);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (STATS) {
-                const int valid = min(BM, M - mt * BM);
-                const int r_end = min(rg * RG + RG, valid);
-                int r = rg * RG;
-                if (r < r_end && !have_k) {
-                    uint32_t u;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stat_base + r * 128 + ((jchunk ^ (r & 7)) << 4)));
-                    k0 = __uint_as_float(u << 16);
-                    k1 = __uint_as_float(u & 0xFFFF0000u);
-                    have_k = true;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> TMA reads
+                __syncwarp();
+                if (lane == 0) {
+                    if (nrows > 0) tma_store_2d(&tm_y, slab, nb * BN + s * 64, mt * BM + q * 32);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                for (; r + 8 <= r_end; r += 8) {
-                    uint32_t u[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)      // r is a multiple of 8 here: (r + i) & 7 == i
-                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[i]) : "r"(stat_base + (r + i) * 128 + ((jchunk ^ i) << 4)));
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float d0 = __uint_as_float(u[i] << 16) - k0;
-                        const float d1 = __uint_as_float(u[i] & 0xFFFF0000u) - k1;
-                        s0 += d0; q0 = fmaf(d0, d0, q0);
-                        s1 += d1; q1 = fmaf(d1, d1, q1);
+                if (STATS && nrows > 0) {
+                    const uint32_t rd = slab + rd_off;
+                    if (!have_k) {
+                        uint32_t u;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(rd + (uint32_t)(rd_chunk << 4)));
+                        k0[s] = __uint_as_float(u << 16);
+                        k1[s] = __uint_as_float(u & 0xFFFF0000u);
                     }
-                    cnt += 8.f;
+                    if (nrows == 32) {
+#pragma unroll
+                        for (int r8 = 0; r8 < 32; r8 += 8) {
+                            uint32_t u[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[i])
+                                             : "r"(rd + (uint32_t)((r8 + i) * 128 + ((rd_chunk ^ i) << 4))));
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float d0 = __uint_as_float(u[i] << 16) - k0[s];
+                                const float d1 = __uint_as_float(u[i] & 0xFFFF0000u) - k1[s];
+                                s0[s] += d0; q0[s] = fmaf(d0, d0, q0[s]);
+                                s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                            }
+                        }
+                    } else {
+                        for (int r = 0; r < nrows; ++r) {
+                            uint32_t u;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u)
+                                         : "r"(rd + (uint32_t)(r * 128 + ((rd_chunk ^ (r & 7)) << 4))));
+                            const float d0 = __uint_as_float(u << 16) - k0[s];
+                            const float d1 = __uint_as_float(u & 0xFFFF0000u) - k1[s];
+                            s0[s] += d0; q0[s] = fmaf(d0, d0, q0[s]);
+                            s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                        }
+                    }
                 }
-                for (; r < r_end; ++r) {
-                    uint32_t u;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stat_base + r * 128 + ((jchunk ^ (r & 7)) << 4)));
-                    const float d0 = __uint_as_float(u << 16) - k0;
-                    const float d1 = __uint_as_float(u & 0xFFFF0000u) - k1;
-                    s0 += d0; q0 = fmaf(d0, d0, q0);
-                    s1 += d1; q1 = fmaf(d1, d1, q1);
-                    cnt += 1.f;
-                }
+                slot = (slot + 1) & (nbuf - 1);      // nbuf is 1 or 2
             }
-            as ^= 1;
-            if (as == 0) aphase ^= 1;
+            if (nrows > 0) { cnt += (float)nrows; have_k = true; }
+            aphase ^= 1;
         }
         if (STATS) {
-            // partial[row][field][N], fields = n, K, sum(y-K), sum((y-K)^2); row = j*G + rg
-            float* p = partial + ((size_t)(j * G + rg) * 4) * N + nb * BN + 2 * w;
-            *reinterpret_cast<float2*>(p) = make_float2(cnt, cnt);
-            *reinterpret_cast<float2*>(p + N) = make_float2(k0, k1);
-            *reinterpret_cast<float2*>(p + 2 * (size_t)N) = make_float2(s0, s1);
-            *reinterpret_cast<float2*>(p + 3 * (size_t)N) = make_float2(q0, q1);
+            // Merge the eight warps' partials (each with its own shift) into ONE row per CTA,
+            // partial[j][field][N] with fields = n, mean, M2 (Chan et al.), so the finalize kernel
+            // reads <= 148 rows.  The store slabs double as scratch once their stores have drained.
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float4* sc = reinterpret_cast<float4*>(sO);
+            const int e = set * 4 + q;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                sc[e * BN + s * 64 + 2 * lane] = make_float4(cnt, k0[s], s0[s], q0[s]);
+                sc[e * BN + s * 64 + 2 * lane + 1] = make_float4(cnt, k1[s], s1[s], q1[s]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int t = (int)threadIdx.x - 64;
+            if (t < BN) {
+                float n_tot = 0.f, m_sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = sc[i * BN + t];
+                    n_tot += v.x;
+                    m_sum += fmaf(v.x, v.y, v.z);                  // n*K + sum(y-K)
+                }
+                const float mu = n_tot > 0.f ? m_sum / n_tot : 0.f;
+                float m2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = sc[i * BN + t];
+                    if (v.x > 0.f) {
+                        const float ds = v.z / v.x;                // mean_i - K_i
+                        const float d = v.y + ds - mu;
+                        m2 += fmaxf(fmaf(-v.z, ds, v.w), 0.f) + v.x * d * d;
+                    }
+                }
+                float* p = partial + (size_t)j * 3 * N + nb * BN + t;
+                p[0] = n_tot;
+                p[N] = mu;
+                p[2 * (size_t)N] = m2;
+            }
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -378,13 +451,13 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)C::TMEM_COLS)
+                     "r"((uint32_t)(2 * BN))
                      : "memory");
     }
 }
 
 // ---------------------------------------------------------------------------
-// statistics finalize: merge R partial rows per channel (Chan et al. pairwise update),
+// statistics finalize: merge the R per-CTA rows (n, mean, M2) per channel (Chan et al.),
 // then the same outputs as bn_stats_finalize_kernel.  1024 threads = 32 row lanes x 32 channels.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -406,9 +479,9 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     float n_sum = 0.f, m_sum = 0.f;
     if (live)
         for (int r = lane; r < R; r += 32) {
-            const float* p = partial + (size_t)r * 4 * C + ch;
-            const float n = p[0];
-            if (n > 0.f) { n_sum += n; m_sum += fmaf(n, p[C], p[2 * (size_t)C]); }   // n*K + S1
+            const float* p = partial + (size_t)r * 3 * C + ch;
+            n_sum += p[0];
+            m_sum = fmaf(p[0], p[C], m_sum);
         }
     sm_a[lane][cl] = n_sum;
     sm_b[lane][cl] = m_sum;
@@ -424,18 +497,13 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     const float n_tot = sm_a[0][cl];
     __syncthreads();
 
-    // pass 2: M2 = sum_p [ S2_p - S1_p^2/n_p + n_p (mean_p - mu)^2 ]
+    // pass 2: M2 = sum_p [ M2_p + n_p (mean_p - mu)^2 ]
     float m2 = 0.f;
     if (live)
         for (int r = lane; r < R; r += 32) {
-            const float* p = partial + (size_t)r * 4 * C + ch;
-            const float n = p[0];
-            if (n > 0.f) {
-                const float s1 = p[2 * (size_t)C];
-                const float mp = p[C] + s1 / n;
-                const float d = mp - mu;
-                m2 += fmaxf(fmaf(-s1, s1 / n, p[3 * (size_t)C]), 0.f) + n * d * d;
-            }
+            const float* p = partial + (size_t)r * 3 * C + ch;
+            const float d = p[C] - mu;
+            m2 += p[2 * (size_t)C] + p[0] * d * d;
         }
     sm_b[lane][cl] = m2;
     __syncthreads();
@@ -490,11 +558,26 @@ bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int b
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int pick_bn(int N) { return (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64); }
+// Tile width: the widest BLOCK_N dividing N unless a narrower one shortens the critical path
+// (waves of row tiles per CTA x BLOCK_N) by more than 10 % -- that only happens when M is small.
+int pick_bn(long long M, int N, int num_sms)
+{
+    const long long m_tiles = (M + BM - 1) / BM;
+    int best = 0;
+    long long best_cost = 0;
+    for (int bn = 256; bn >= 64; bn >>= 1) {
+        if (N % bn) continue;
+        long long per = num_sms / (N / bn);
+        if (per < 1) per = 1;
+        const long long cost = ((m_tiles + per - 1) / per) * bn;
+        if (best == 0 || cost * 10 < best_cost * 9) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
 
 void grid_shape(long long M, int N, int num_sms, int& bn, int& ctas_per_n, int& grid)
 {
-    bn = pick_bn(N);
+    bn = pick_bn(M, N, num_sms);
     const int n_blocks = N / bn;
     const long long m_tiles = (M + BM - 1) / BM;
     long long per = num_sms / n_blocks;
@@ -504,14 +587,45 @@ void grid_shape(long long M, int N, int num_sms, int& bn, int& ctas_per_n, int& 
     grid = n_blocks * ctas_per_n;
 }
 
+// Shared-memory plan.  W stays resident when the CTA's [BN, K] block plus a >= 3-deep X ring
+// fits (then every row tile costs one 16 KB X load instead of X + W); the store slabs shrink
+// from 2 to 1 per warp if that is what makes it fit.
+C1Plan make_plan(int bn, int K, int n_blocks, int& smem_bytes)
+{
+    const int k_blocks = (K + BK - 1) / BK;
+    const int b_bytes = bn * BK * 2;
+    C1Plan p;
+    p.x_hint_first = n_blocks == 1;
+    p.resident = 0;
+    p.nbuf = 2;
+    for (int nbuf = 2; nbuf >= 1 && !p.resident; --nbuf) {
+        const int ring = SMEM_LIMIT - SMEM_FIXED - 8 * nbuf * SLAB_BYTES - k_blocks * b_bytes;
+        if (ring >= 3 * A_BYTES) { p.resident = 1; p.nbuf = nbuf; }
+    }
+    const int stage_bytes = A_BYTES + (p.resident ? 0 : b_bytes);
+    const int ring = SMEM_LIMIT - SMEM_FIXED - 8 * p.nbuf * SLAB_BYTES - (p.resident ? k_blocks * b_bytes : 0);
+    p.stages = ring / stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    smem_bytes = SMEM_FIXED + (p.resident ? k_blocks * b_bytes : 0) + p.stages * stage_bytes +
+                 8 * p.nbuf * SLAB_BYTES;
+    return p;
+}
+
 template <int BN>
 cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, int M, int N, int K,
                    float* partial, int grid, cudaStream_t st)
 {
     auto kern = partial ? c1_gemm_kernel<BN, true> : c1_gemm_kernel<BN, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, kThreads, Cfg<BN>::SMEM, st>>>(tx, tw, ty, M, N, K, partial);
+    static bool configured[2] = {false, false};
+    if (!configured[partial ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        configured[partial ? 1 : 0] = true;
+    }
+    int smem = 0;
+    const C1Plan plan = make_plan(BN, K, N / BN, smem);
+    if (plan.stages < 2) return cudaErrorInvalidValue;
+    kern<<<grid, kThreads, smem, st>>>(tx, tw, ty, M, N, K, partial, plan);
     return cudaGetLastError();
 }
 
@@ -530,10 +644,10 @@ int c1_partial_rows(long long M, int N, int num_sms)
 {
     int bn, per, grid;
     grid_shape(M, N, num_sms, bn, per, grid);
-    return per * (kEpiThreads / (bn / 2));
+    return per;              // one merged partial row per CTA
 }
 
-// y[M,N] = x[M,K] . w[N,K]^T (bf16); partial (nullable) = [c1_partial_rows][4][N] fp32
+// y[M,N] = x[M,K] . w[N,K]^T (bf16); partial (nullable) = [c1_partial_rows][3][N] fp32
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
                            int num_sms, cudaStream_t st)
 {
@@ -541,7 +655,7 @@ cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, i
     int bn, per, grid;
     grid_shape(M, N, num_sms, bn, per, grid);
     CUtensorMap tx, tw, ty;
-    if (!make_map(&tx, x, M, K, BM) || !make_map(&tw, w, N, K, bn) || !make_map(&ty, y, M, N, BM))
+    if (!make_map(&tx, x, M, K, BM) || !make_map(&tw, w, N, K, bn) || !make_map(&ty, y, M, N, 32))
         return cudaErrorInvalidValue;
     switch (bn) {
     case 256: return launch<256>(tx, tw, ty, (int)M, N, K, partial, grid, st);

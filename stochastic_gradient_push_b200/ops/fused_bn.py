@@ -34,7 +34,7 @@ FORCE_REFERENCE = False      # debugging / A-B switch: route everything to the P
 # 1x1 convolutions feeding a training-mode BatchNorm run as the tcgen05 GEMM with the
 # statistics fused into its epilogue (csrc/conv1x1_kernels.cu).  SGP_B200_CONV1X1=0 routes
 # them back to the library convolution + stand-alone statistics pass.
-USE_TCGEN05_CONV1X1 = os.environ.get('SGP_B200_CONV1X1', '0') != '0'
+USE_TCGEN05_CONV1X1 = os.environ.get('SGP_B200_CONV1X1', '1') != '0'
 
 
 def _can_fuse(x: torch.Tensor) -> bool:

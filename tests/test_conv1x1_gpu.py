@@ -11,9 +11,9 @@ from stochastic_gradient_push_b200.ops.fused_bn import FusedBatchNormAct2d, conv
 pytestmark = pytest.mark.gpu
 
 # (M, K, N): one tile / ragged last tile / several k-blocks / every BLOCK_N / more n-blocks than
-# m-tiles / ResNet-50 layer shapes at a small batch
+# m-tiles / resident-W with 2 store slabs / ResNet-50 layer shapes at a small batch / K % 64 != 0
 GEMM_SHAPES = [(128, 64, 64), (677, 64, 64), (1000, 256, 128), (4096, 128, 256), (3000, 512, 512),
-               (130, 192, 1024), (25088, 64, 256), (6272, 1024, 256), (1568, 2048, 512), (40000, 72, 192)]
+               (130, 192, 1024), (4224, 256, 256), (2000, 1024, 64), (25088, 64, 256), (6272, 1024, 256), (1568, 2048, 512), (40000, 72, 192)]
 
 
 def _mats(M, K, N, x_mean=0.0):
