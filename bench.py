@@ -174,6 +174,13 @@ def run_ours(args):
     n_bn = sum(isinstance(m, FusedBatchNormAct2d) for m in net.modules())
     n_pool = sum(isinstance(m, MaxPool2dNHWC) for m in net.modules())
     kernels_per_step += 6 * n_bn + 2 * n_pool
+    # (for 1x1 convolutions the "stats" launch is the tcgen05 GEMM whose epilogue produces them);
+    # + stem convolution forward / wgrad, + one dgrad GEMM (skip gradient folded in) per bottleneck
+    from stochastic_gradient_push_b200.ops import fused_bn as _fb
+    from stochastic_gradient_push_b200.models.resnet import Bottleneck
+    kernels_per_step += 2
+    if _fb.USE_TCGEN05_CONV1X1:
+        kernels_per_step += sum(isinstance(m, Bottleneck) for m in net.modules())
 
     # synthetic data: a small pool of pinned host batches (the loader's output)
     g = torch.Generator().manual_seed(1234 + rank)
@@ -247,6 +254,8 @@ def run_ours(args):
                        'bf16_path': ('autocast' if (args.autocast or args.algo == 'ar') else
                                      'shadow weights written by the gossip kernel'),
                        'cuda_graph': not args.no_graph,
+                       'conv1x1': ('tcgen05 GEMM (TMA/TMEM), BN statistics and skip gradient fused '
+                                   'into its epilogues' if _fb.USE_TCGEN05_CONV1X1 else 'library'),
                        'l2': 'per-step working set (activations+weights > 1 GB) exceeds the '
                              '126 MB L2; no explicit flush'},
             'clocks': clocks, 'e2e': e2e,

@@ -24,7 +24,8 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
-from ..ops.fused_bn import FusedBatchNormAct2d as _BN, MaxPool2dNHWC, conv_bn_act, stem_conv
+from ..ops.fused_bn import (FusedBatchNormAct2d as _BN, MaxPool2dNHWC, conv_bn_act, conv_bn_act_split,
+                             stem_conv)
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -76,8 +77,9 @@ class Bottleneck(nn.Module):
         return self.bn3
 
     def forward(self, x):
-        identity = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
-        out = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        # x feeds conv1 and the skip branch: the split op folds the skip gradient into conv1's dgrad
+        out, skip = conv_bn_act_split(self.conv1, self.bn1, x, relu=True)
+        identity = skip if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], skip)
         out = self.bn2(self.conv2(out), relu=True)
         return conv_bn_act(self.conv3, self.bn3, out, residual=identity, relu=True)
 

@@ -256,7 +256,7 @@ extern "C" {
 int c1_supported(long long M, int N, int K);
 int c1_partial_rows(long long M, int N, int num_sms);
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
-                           int num_sms, cudaStream_t st);
+                           const void* residual, int num_sms, cudaStream_t st);
 cudaError_t c1_launch_stats_finalize(const float* partial, int R, int C, const float* gamma, const float* beta,
                                      float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                                      float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
@@ -287,20 +287,30 @@ static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
 
 static int sm_count() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
 
+// y = x . w^T [+ residual] (residual: same shape / layout as y, added in fp32 in the epilogue).
 // with_stats: also run the statistics epilogue into a scratch buffer (benchmarking the GEMM alone)
-static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w, bool with_stats)
+static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w, bool with_stats,
+                                     c10::optional<torch::Tensor> residual)
 {
     TORCH_CHECK(conv1x1_can_fuse(x, w), "conv1x1_forward: unsupported tensors");
     const int K = (int)x.size(1), N = (int)w.size(0);
     const long long M = x.numel() / K;
     c10::cuda::CUDAGuard guard(x.get_device());
     auto y = conv1x1_alloc_out(x, N);
+    const bool has_res = residual.has_value() && residual->defined();
+    TORCH_CHECK(!(has_res && with_stats));
+    if (has_res)
+        TORCH_CHECK(residual->is_cuda() && residual->scalar_type() == torch::kBFloat16 &&
+                    residual->sizes() == y.sizes() && residual->strides() == y.strides() &&
+                    (reinterpret_cast<uintptr_t>(residual->data_ptr()) & 15) == 0,
+                    "conv1x1_forward: residual must match the output's shape and layout");
     torch::Tensor partial;
     if (with_stats)
         partial = torch::empty({c1_partial_rows(M, N, sm_count()), 3, N},
                                torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
     BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K,
-                            with_stats ? partial.data_ptr<float>() : nullptr, sm_count(),
+                            with_stats ? partial.data_ptr<float>() : nullptr,
+                            has_res ? residual->data_ptr() : nullptr, sm_count(),
                             at::cuda::getCurrentCUDAStream()));
     return y;
 }
@@ -330,7 +340,7 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
     const int R = c1_partial_rows(M, N, sms);
     auto partial = torch::empty({R, 3, N}, fopt);
     BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), yraw.data_ptr(), M, N, K, partial.data_ptr<float>(),
-                            sms, st));
+                            nullptr, sms, st));
     auto coef = torch::empty({4, N}, fopt);      // mean, invstd, scale, shift
     float* mean = coef.data_ptr<float>();
     float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
@@ -353,7 +363,8 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
 void bind_bn(py::module& mod)
 {
     mod.def("conv1x1_can_fuse", &conv1x1_can_fuse);
-    mod.def("conv1x1_forward", &conv1x1_forward, py::arg("x"), py::arg("w"), py::arg("with_stats") = false);
+    mod.def("conv1x1_forward", &conv1x1_forward, py::arg("x"), py::arg("w"), py::arg("with_stats") = false,
+            py::arg("residual") = py::none());
     mod.def("conv1x1_bn_forward", &conv1x1_bn_forward);
     mod.def("stem_can_fuse", &stem_can_fuse);
     mod.def("stem_forward", &stem_forward);

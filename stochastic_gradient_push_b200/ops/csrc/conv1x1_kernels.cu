@@ -53,7 +53,7 @@ constexpr int SLAB_BYTES = 32 * 128;    // one epilogue warp's store slab: 32 ro
 constexpr int kThreads = 320;           // producer warp, MMA warp, 2 x 4 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
-constexpr int SMEM_FIXED = 1024 + 256;  // alignment slack + barriers / TMEM slot
+constexpr int SMEM_FIXED = 1024 + 512;  // alignment slack + barriers / TMEM slot
 
 // cute::TMA::CacheHintSm90 encodings
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
@@ -113,6 +113,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_s(const CUtensorMap* tm, uint32_t bar_smem, uint32_t dst_smem, int c0,
+                                              int c1, uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_smem), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1)
@@ -191,12 +200,15 @@ struct C1Plan {            // host-computed shared-memory plan (bytes are multip
     int x_hint_first;      // 1: X tiles are read by one CTA only -> L2 evict_first
 };
 
-template <int BN, bool STATS>
+// MODE 0: Y = X.W^T          MODE 1: + BatchNorm statistics of Y          MODE 2: Y = X.W^T + R
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_y, int M, int N, int K, float* __restrict__ partial,
-               const C1Plan plan)
+               const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r, int M, int N,
+               int K, float* __restrict__ partial, const C1Plan plan)
 {
+    constexpr bool STATS = MODE == 1;
+    constexpr bool RES = MODE == 2;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int NS = BN / 64;               // 64-column sub-tiles per tile
     extern __shared__ uint8_t smem_raw[];
@@ -224,7 +236,8 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     uint64_t* tfull = empty + MAX_STAGES;    // accumulator stage ready for the epilogue
     uint64_t* tempty = tfull + 2;            // accumulator stage drained
     uint64_t* wfull = tempty + 2;            // resident W landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    uint64_t* rbar0 = wfull + 1;             // MODE 2: residual slab landed, [8 warps][2 slots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar0 + 16);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -233,6 +246,7 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         mbar_init(wfull, 1);
+        if (RES) { tma_prefetch_desc(&tm_r); for (int i = 0; i < 16; ++i) mbar_init(&rbar0[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -306,8 +320,8 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     } else {
         // ===================== epilogue =====================
         // Two sets of four warps; set h drains accumulator stage h, i.e. every other tile, so each
-        // SM sub-partition always has two epilogue warps to interleave (one warp per scheduler
-        // exposes every TMEM / smem latency: ncu showed the statistics loop running at IPC ~0.4).
+        // SM sub-partition has two epilogue warps to interleave (a lone warp per scheduler exposes
+        // every TMEM / shared-memory latency) and one stage drains while the other fills.
         // Within a set, warp q owns tile rows [32q, 32q+32) (its TMEM lane quadrant) end to end:
         // TMEM -> bf16 -> its own 4 KB swizzled slab -> its own TMA store (box 64 x 32) ->
         // statistics of exactly those rows read back from the slab.  No CTA-wide barrier; slabs
@@ -326,7 +340,20 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         bool have_k = false;
         const int as = set;
         uint32_t aphase = 0;
-        for (int mt = j + set * ctas_per_n; mt < m_tiles; mt += 2 * ctas_per_n) {
+        // MODE 2: the residual slab of sub-tile i+1 is fetched (TMA, own mbarrier per slab) while
+        // sub-tile i is converted; the sum is formed in fp32 in place and stored from the same slab.
+        const uint32_t rbar = smem_u32(rbar0 + (set * 4 + q) * 2);
+        uint32_t rphase = 0;                                     // bit b: parity of slab b's barrier
+        const int tile_step = 2 * ctas_per_n;
+        if (RES && lane == 0) {
+            const int mt0 = j + set * ctas_per_n;
+            if (mt0 < m_tiles && M - mt0 * BM - q * 32 > 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar), "r"(SLAB_BYTES)
+                             : "memory");
+                tma_load_2d_s(&tm_r, rbar, slab0, nb * BN, mt0 * BM + q * 32, L2_EVICT_FIRST);
+            }
+        }
+        for (int mt = j + set * ctas_per_n; mt < m_tiles; mt += tile_step) {
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const int nrows = min(32, M - mt * BM - q * 32);       // rows of this slab that exist (<= 0: none)
@@ -334,11 +361,13 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 const uint32_t slab = slab0 + (uint32_t)(slot * SLAB_BYTES);
-                if (lane == 0) {                                   // the store that last used this slab has read it
-                    if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (!RES) {
+                    if (lane == 0) {                               // the store that last used this slab has read it
+                        if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 uint32_t v[64];
                 tmem_ld32(t_row + (uint32_t)(s * 64), v);
                 tmem_ld32(t_row + (uint32_t)(s * 64 + 32), v + 32);
@@ -348,19 +377,61 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
+                if (RES && nrows > 0) {
+                    const uint32_t bar = rbar + (uint32_t)(slot * 8);
+                    const uint32_t par = (rphase >> slot) & 1u;
+                    while (true) {
+                        uint32_t ok;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+                        if (ok) break;
+                    }
+                    rphase ^= 1u << slot;
+                }
+                if (!RES || nrows > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t chunk = (uint32_t)(i ^ (lane & 7));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + wr_off + chunk * 16),
-                                 "r"(pack_bf16(v[8 * i + 0], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
-                                 "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
-                                 : "memory");
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t addr = slab + wr_off + (uint32_t)((i ^ (lane & 7)) * 16);
+                        if (RES) {
+                            uint32_t r0, r1, r2, r3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+                            const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[8 * i + 2 * e] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e]) +
+                                                                   __uint_as_float(rr[e] << 16));
+                                v[8 * i + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e + 1]) +
+                                                                       __uint_as_float(rr[e] & 0xFFFF0000u));
+                            }
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                                     "r"(pack_bf16(v[8 * i + 0], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
+                                     "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
+                                     : "memory");
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> TMA reads
                 __syncwarp();
                 if (lane == 0) {
                     if (nrows > 0) tma_store_2d(&tm_y, slab, nb * BN + s * 64, mt * BM + q * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (RES) {                                     // fetch the next residual slab
+                        const int nmt = (s + 1 < NS) ? mt : mt + tile_step;
+                        const int ns = (s + 1 < NS) ? s + 1 : 0;
+                        if (nmt < m_tiles && M - nmt * BM - q * 32 > 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // other slab is free
+                            const uint32_t nbar = rbar + (uint32_t)((slot ^ 1) * 8);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nbar),
+                                         "r"(SLAB_BYTES)
+                                         : "memory");
+                            tma_load_2d_s(&tm_r, nbar, slab0 + (uint32_t)((slot ^ 1) * SLAB_BYTES), nb * BN + ns * 64,
+                                          nmt * BM + q * 32, L2_EVICT_FIRST);
+                        }
+                    }
                 }
                 if (STATS && nrows > 0) {
                     const uint32_t rd = slab + rd_off;
@@ -590,7 +661,7 @@ void grid_shape(long long M, int N, int num_sms, int& bn, int& ctas_per_n, int& 
 // Shared-memory plan.  W stays resident when the CTA's [BN, K] block plus a >= 3-deep X ring
 // fits (then every row tile costs one 16 KB X load instead of X + W); the store slabs shrink
 // from 2 to 1 per warp if that is what makes it fit.
-C1Plan make_plan(int bn, int K, int n_blocks, int& smem_bytes)
+C1Plan make_plan(int bn, int K, int n_blocks, bool residual, int& smem_bytes)
 {
     const int k_blocks = (K + BK - 1) / BK;
     const int b_bytes = bn * BK * 2;
@@ -598,7 +669,7 @@ C1Plan make_plan(int bn, int K, int n_blocks, int& smem_bytes)
     p.x_hint_first = n_blocks == 1;
     p.resident = 0;
     p.nbuf = 2;
-    for (int nbuf = 2; nbuf >= 1 && !p.resident; --nbuf) {
+    for (int nbuf = 2; nbuf >= (residual ? 2 : 1) && !p.resident; --nbuf) {   // MODE 2 double-buffers its slabs
         const int ring = SMEM_LIMIT - SMEM_FIXED - 8 * nbuf * SLAB_BYTES - k_blocks * b_bytes;
         if (ring >= 3 * A_BYTES) { p.resident = 1; p.nbuf = nbuf; }
     }
@@ -612,20 +683,20 @@ C1Plan make_plan(int bn, int K, int n_blocks, int& smem_bytes)
 }
 
 template <int BN>
-cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, int M, int N, int K,
-                   float* partial, int grid, cudaStream_t st)
+cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
+                   int M, int N, int K, float* partial, int mode, int grid, cudaStream_t st)
 {
-    auto kern = partial ? c1_gemm_kernel<BN, true> : c1_gemm_kernel<BN, false>;
-    static bool configured[2] = {false, false};
-    if (!configured[partial ? 1 : 0]) {
+    auto kern = mode == 1 ? c1_gemm_kernel<BN, 1> : (mode == 2 ? c1_gemm_kernel<BN, 2> : c1_gemm_kernel<BN, 0>);
+    static bool configured[3] = {false, false, false};
+    if (!configured[mode]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
-        configured[partial ? 1 : 0] = true;
+        configured[mode] = true;
     }
     int smem = 0;
-    const C1Plan plan = make_plan(BN, K, N / BN, smem);
+    const C1Plan plan = make_plan(BN, K, N / BN, mode == 2, smem);
     if (plan.stages < 2) return cudaErrorInvalidValue;
-    kern<<<grid, kThreads, smem, st>>>(tx, tw, ty, M, N, K, partial, plan);
+    kern<<<grid, kThreads, smem, st>>>(tx, tw, ty, tr, M, N, K, partial, plan);
     return cudaGetLastError();
 }
 
@@ -647,20 +718,23 @@ int c1_partial_rows(long long M, int N, int num_sms)
     return per;              // one merged partial row per CTA
 }
 
-// y[M,N] = x[M,K] . w[N,K]^T (bf16); partial (nullable) = [c1_partial_rows][3][N] fp32
+// y[M,N] = x[M,K] . w[N,K]^T (bf16) [+ residual[M,N]]; partial (nullable) = [c1_partial_rows][3][N] fp32
+// statistics of y.  partial and residual are mutually exclusive.
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
-                           int num_sms, cudaStream_t st)
+                           const void* residual, int num_sms, cudaStream_t st)
 {
-    if (!c1_supported(M, N, K)) return cudaErrorInvalidValue;
+    if (!c1_supported(M, N, K) || (partial && residual)) return cudaErrorInvalidValue;
+    const int mode = partial ? 1 : (residual ? 2 : 0);
     int bn, per, grid;
     grid_shape(M, N, num_sms, bn, per, grid);
-    CUtensorMap tx, tw, ty;
-    if (!make_map(&tx, x, M, K, BM) || !make_map(&tw, w, N, K, bn) || !make_map(&ty, y, M, N, 32))
+    CUtensorMap tx, tw, ty, tr;
+    if (!make_map(&tx, x, M, K, BM) || !make_map(&tw, w, N, K, bn) || !make_map(&ty, y, M, N, 32) ||
+        !make_map(&tr, residual ? residual : y, M, N, 32))
         return cudaErrorInvalidValue;
     switch (bn) {
-    case 256: return launch<256>(tx, tw, ty, (int)M, N, K, partial, grid, st);
-    case 128: return launch<128>(tx, tw, ty, (int)M, N, K, partial, grid, st);
-    default: return launch<64>(tx, tw, ty, (int)M, N, K, partial, grid, st);
+    case 256: return launch<256>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+    case 128: return launch<128>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+    default: return launch<64>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
     }
 }
 

@@ -155,28 +155,97 @@ class _Conv1x1BNAct(torch.autograd.Function):
         return dx, dw, (dz if ctx.add else None), ggamma, gbeta, None, None, None, None, None, None
 
 
-def conv_bn_act(conv: nn.Conv2d, bn: 'FusedBatchNormAct2d', x, residual=None, relu=False):
-    """``bn(conv(x), residual=residual, relu=relu)``; 1x1 / stride-1 convolutions of NHWC bf16
-    activations in training mode take the fused tcgen05 path."""
-    if (USE_TCGEN05_CONV1X1 and not FORCE_REFERENCE and bn.training and bn.track_running_stats
+class _Conv1x1BNActSplit(torch.autograd.Function):
+    """``(act(bn(conv1x1(x, w))), x)`` for a block input that also feeds the skip connection.
+    Returning ``x`` through the op routes the skip-branch gradient into ``backward``, where the
+    dgrad GEMM adds it in its epilogue (fp32, before rounding) instead of autograd running a
+    separate read-read-write accumulation pass over the widest activation of the block."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu):
+        C = native.load()
+        w16 = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        yraw, out, coef = C.conv1x1_bn_forward(x, w16, None, gamma, beta, running_mean, running_var,
+                                               nbt, momentum, eps, relu)
+        ctx.relu = relu
+        ctx.w_dtype = w.dtype
+        ctx.save_for_backward(x, w16, yraw, coef)
+        ctx.set_materialize_grads(False)
+        return out, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, d_out, d_skip):
+        C = native.load()
+        x, w16, yraw, coef = ctx.saved_tensors
+        if d_out is None:
+            d_out = torch.zeros_like(yraw)
+        dyraw, _, ggamma, gbeta = C.bn_backward(d_out, yraw, None, coef, ctx.relu, False)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # dX = dY . W: the same GEMM with the transposed weight as its K-major B operand
+            wt = w16.reshape(w16.shape[0], w16.shape[1]).t().contiguous()
+            res = d_skip
+            if res is not None and (res.dtype != torch.bfloat16
+                                    or not res.is_contiguous(memory_format=torch.channels_last)):
+                res = res.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            if C.conv1x1_can_fuse(dyraw, wt):
+                dx = C.conv1x1_forward(dyraw, wt, False, res)
+            else:
+                dx = torch.ops.aten.convolution_backward(
+                    dyraw, x, w16, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+                if res is not None:
+                    dx = dx + res
+        if ctx.needs_input_grad[1]:
+            dw = torch.ops.aten.convolution_backward(
+                dyraw, x, w16, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            if dw.dtype != ctx.w_dtype:
+                dw = dw.to(ctx.w_dtype)
+        return dx, dw, ggamma, gbeta, None, None, None, None, None, None
+
+
+def _conv1x1_operands(conv, bn, x, residual, relu):
+    """(x, fusable): x possibly cast the way autocast would; fusable says whether the tcgen05
+    conv + BN path covers this call."""
+    if not (USE_TCGEN05_CONV1X1 and not FORCE_REFERENCE and bn.training and bn.track_running_stats
             and x.is_cuda and native.available() and x.dim() == 4
             and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
             and conv.groups == 1 and conv.bias is None and bn.weight is not None
             and bn.weight.dtype == torch.float32 and (residual is None or relu)):
-        w = conv.weight
-        if x.dtype == torch.float32 and torch.is_autocast_enabled():
-            x = x.to(torch.bfloat16)
-        if x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last) \
-                and (w.dtype == torch.bfloat16 or torch.is_autocast_enabled()) \
-                and (residual is None or (residual.dtype == torch.bfloat16
-                                          and residual.is_contiguous(memory_format=torch.channels_last))):
-            C = native.load()
-            wk = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
-            if C.conv1x1_can_fuse(x, wk) and conv.out_channels % 8 == 0:
-                momentum = 0.1 if bn.momentum is None else bn.momentum
-                return _Conv1x1BNAct.apply(x, w, residual, bn.weight, bn.bias, bn.running_mean,
-                                           bn.running_var, bn.num_batches_tracked, momentum, bn.eps, relu)
+        return x, False
+    w = conv.weight
+    if x.dtype == torch.float32 and torch.is_autocast_enabled():
+        x = x.to(torch.bfloat16)
+    if not (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+            and (w.dtype == torch.bfloat16 or torch.is_autocast_enabled())
+            and (residual is None or (residual.dtype == torch.bfloat16
+                                      and residual.is_contiguous(memory_format=torch.channels_last)))):
+        return x, False
+    wk = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+    return x, bool(native.load().conv1x1_can_fuse(x, wk)) and conv.out_channels % 8 == 0
+
+
+def conv_bn_act(conv: nn.Conv2d, bn: 'FusedBatchNormAct2d', x, residual=None, relu=False):
+    """``bn(conv(x), residual=residual, relu=relu)``; 1x1 / stride-1 convolutions of NHWC bf16
+    activations in training mode take the fused tcgen05 path."""
+    xk, ok = _conv1x1_operands(conv, bn, x, residual, relu)
+    if ok:
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        return _Conv1x1BNAct.apply(xk, conv.weight, residual, bn.weight, bn.bias, bn.running_mean,
+                                   bn.running_var, bn.num_batches_tracked, momentum, bn.eps, relu)
     return bn(conv(x), residual=residual, relu=relu)
+
+
+def conv_bn_act_split(conv: nn.Conv2d, bn: 'FusedBatchNormAct2d', x, relu=False):
+    """``(bn(conv(x), relu=relu), x)`` for an ``x`` that is also consumed by a skip connection:
+    use the returned ``x`` for the skip branch and its gradient is added inside the dgrad GEMM
+    of ``conv`` (see :class:`_Conv1x1BNActSplit`).  Falls back to ``(conv_bn_act(...), x)``."""
+    if x.requires_grad and torch.is_grad_enabled():
+        xk, ok = _conv1x1_operands(conv, bn, x, None, relu)
+        if ok and xk is x:
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            return _Conv1x1BNActSplit.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean,
+                                            bn.running_var, bn.num_batches_tracked, momentum, bn.eps, relu)
+    return conv_bn_act(conv, bn, x, relu=relu), x
 
 
 # --------------------------------------------------------------------------- #

@@ -65,6 +65,22 @@ def test_fused_statistics_match_two_pass(M, K, N, x_mean):
         torch.testing.assert_close(rv, 0.9 + 0.1 * var * M / (M - 1), rtol=2e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('M,K,N', GEMM_SHAPES)
+def test_gemm_residual_epilogue(M, K, N):
+    """y = x . w^T + r with the sum formed in fp32 before the single bf16 rounding."""
+    C = native.load()
+    x, w = _mats(M, K, N)
+    g = torch.Generator(device='cuda').manual_seed(7)
+    r = (torch.randn(M, N, device='cuda', generator=g) * 2).to(torch.bfloat16)
+    y = C.conv1x1_forward(x, w, False, r)
+    torch.cuda.synchronize()
+    want = x.float() @ w.float().t() + r.float()
+    torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=2e-2)
+    # strictly better than rounding twice would allow on average
+    twice = (x.float() @ w.float().t()).to(torch.bfloat16).float() + r.float()
+    assert (y.float() - want).abs().mean() <= (twice.to(torch.bfloat16).float() - want).abs().mean() * 1.05
+
+
 def _block(cin, cout, seed):
     torch.manual_seed(seed)
     conv = nn.Conv2d(cin, cout, 1, bias=False).cuda().to(memory_format=torch.channels_last)
@@ -136,3 +152,47 @@ def test_unsupported_inputs_fall_back(monkeypatch):
     bn.eval()
     y = conv_bn_act(conv, bn, x.contiguous(memory_format=torch.channels_last), relu=True)
     assert y.shape == (2, 128, 8, 8)
+
+
+@pytest.mark.parametrize('cin,width,hw', [(256, 64, 14), (64, 64, 9), (512, 128, 7)])
+@pytest.mark.parametrize('downsample', [False, True])
+def test_bottleneck_split_backward_matches_unfused(monkeypatch, cin, width, hw, downsample):
+    """A whole bottleneck block (conv1 dgrad absorbs the skip gradient) vs the library path:
+    outputs, input gradient and every parameter gradient."""
+    from stochastic_gradient_push_b200.models.resnet import Bottleneck, _conv1x1, _BN
+    results = []
+    for use in (True, False):
+        monkeypatch.setattr(fused_bn, 'USE_TCGEN05_CONV1X1', use)
+        torch.manual_seed(5)
+        ds = None
+        if downsample or cin != 4 * width:
+            ds = nn.Sequential(_conv1x1(cin, 4 * width), _BN(4 * width))
+        blk = Bottleneck(cin, width, 1, ds).cuda().to(memory_format=torch.channels_last)
+        for m in blk.modules():
+            if isinstance(m, nn.Conv2d):
+                m.to(torch.bfloat16)
+        with torch.no_grad():
+            for m in blk.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.weight.uniform_(0.5, 1.5)
+                    m.bias.normal_(0, 0.1)
+        g = torch.Generator(device='cuda').manual_seed(2)
+        x0 = torch.randn(8, cin, hw, hw, device='cuda', generator=g).to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        x = x0 * 1                      # non-leaf block input, as inside the network
+        y = blk(x)
+        dy = torch.randn(y.shape, device='cuda', generator=g).to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        results.append(dict(y=y.detach().float(), dx=x0.grad.float(),
+                            grads={n: p.grad.float() for n, p in blk.named_parameters()}))
+    got, want = results
+    for key in ('y', 'dx'):
+        bad = (got[key] - want[key]).abs() > 5e-2 + 5e-2 * want[key].abs()
+        assert bad.float().mean().item() < 2e-3, key
+    # a ReLU mask that flips on a 1-ulp difference moves one channel's gamma gradient by a whole
+    # term at these tiny batch sizes, so parameter gradients are compared in relative L2 norm
+    for n in want['grads']:
+        rel = (got['grads'][n] - want['grads'][n]).norm().item() / (want['grads'][n].norm().item() + 1e-6)
+        assert rel < 3e-2, (n, rel)
