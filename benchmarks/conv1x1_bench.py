@@ -3,6 +3,9 @@
     library conv  + fused-BN (stats pass + finalize + apply)      <- default path
     tcgen05 GEMM with the statistics in its epilogue + finalize + apply
 
+and of the conv1 dgrad of every bottleneck (library dgrad + gradient-accumulation add vs the
+same GEMM with the skip gradient added in its epilogue).
+
 CUDA-event timing, L2 flushed between iterations, median of ``--iters`` runs.
 
     python benchmarks/conv1x1_bench.py --batch 256 --out gpurun_out/conv1x1_bench.json
@@ -26,6 +29,13 @@ LAYERS = [
     (56, 256, 128, False, 1), (28, 128, 512, True, 4), (28, 512, 128, False, 3),
     (28, 512, 256, False, 1), (14, 256, 1024, True, 6), (14, 1024, 256, False, 5),
     (14, 1024, 512, False, 1), (7, 512, 2048, True, 3), (7, 2048, 512, False, 2),
+]
+
+
+# (H=W, width = C_out of conv1, C_in = block input channels) of conv1 in the 16 bottlenecks
+DGRAD_LAYERS = [
+    (56, 64, 64, 1), (56, 64, 256, 2), (56, 128, 256, 1), (28, 128, 512, 3),
+    (28, 256, 512, 1), (14, 256, 1024, 5), (14, 512, 1024, 1), (7, 512, 2048, 2),
 ]
 
 
@@ -84,11 +94,42 @@ def main():
                   hw, hw, cin, cout, add, mult, out['library'], out['tcgen05'], out['lib_conv_only'],
                   rows[-1]['lib_conv_tbps'], out['tc_gemm_only'], rows[-1]['gemm_tbps'], out['tc_gemm_stats']), flush=True)
     print('ResNet-50 fwd 1x1 conv+BN total: library %.3f ms, tcgen05 %.3f ms' % (tot_lib, tot_tc))
+
+    # backward of the first 1x1 convolution of every bottleneck: dX = dY . W (+ skip gradient)
+    drows, d_lib, d_tc = [], 0.0, 0.0
+    for hw, width, cin, mult in DGRAD_LAYERS:
+        dy = torch.randn(args.batch, width, hw, hw, device='cuda').to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        skip = torch.randn(args.batch, cin, hw, hw, device='cuda').to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        xin = torch.empty_like(skip)
+        w = (torch.randn(width, cin, 1, 1, device='cuda') * cin ** -0.5).to(torch.bfloat16)
+        C = native.load()
+
+        def lib():
+            dx = torch.ops.aten.convolution_backward(dy, xin, w, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+                                                     [True, False, False])[0]
+            return dx.add_(skip)
+
+        def fused():
+            wt = w.reshape(width, cin).t().contiguous()
+            return C.conv1x1_forward(dy, wt, False, skip)
+
+        with torch.no_grad():
+            for _ in range(3):
+                lib(); fused()
+            t_lib, t_tc = timed(lib, args.iters, flush), timed(fused, args.iters, flush)
+        drows.append(dict(hw=hw, width=width, cin=cin, mult=mult, library=t_lib, tcgen05=t_tc))
+        d_lib += mult * t_lib
+        d_tc += mult * t_tc
+        print('dgrad %3dx%-3d %4d->%-4d x%d | lib dgrad + add %.3f ms | tcgen05 dgrad(+skip) %.3f ms' % (
+            hw, hw, width, cin, mult, t_lib, t_tc), flush=True)
+    print('ResNet-50 conv1 dgrad + skip-gradient accumulation total: library %.3f ms, tcgen05 %.3f ms' % (d_lib, d_tc))
     if args.out:
         os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
         with open(args.out, 'w') as f:
-            json.dump(dict(batch=args.batch, total_library_ms=tot_lib, total_tcgen05_ms=tot_tc, layers=rows), f,
-                      indent=1)
+            json.dump(dict(batch=args.batch, total_library_ms=tot_lib, total_tcgen05_ms=tot_tc, layers=rows,
+                           dgrad_library_ms=d_lib, dgrad_tcgen05_ms=d_tc, dgrad_layers=drows), f, indent=1)
 
 
 if __name__ == '__main__':
