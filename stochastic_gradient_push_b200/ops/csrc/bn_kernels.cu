@@ -125,6 +125,7 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
 // L2-latency-bound loads took ~78 us per launch -- longer than the streaming
 // kernels it finalises).
 #define BN_FIN_THREADS 1024
+#define BN_FIN_ILP 10          // rows per lane in flight (G <= 592 -> 19 rows per lane: two batches)
 
 __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int G, int C,
                                              float& s_out, float& q_out, bool& owner, int& ch)
@@ -134,18 +135,25 @@ __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, 
     const int cl = threadIdx.x & 31;
     const int lane = threadIdx.x >> 5;
     ch = blockIdx.x * 32 + cl;
+    // All of a lane's rows are requested before any is consumed: the partials sit in L2, each
+    // dependent load costs ~0.7 us, and a two-deep loop made these kernels 8-13 us each --
+    // 106 launches, ~5 % of the training step (profiles/launches_r1_bs256_final.csv).
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
     if (ch < C) {
-        int g = lane;
-        for (; g + 32 < G; g += 64) {
-            s0 += partial[(size_t)g * 2 * C + ch];
-            q0 += partial[(size_t)g * 2 * C + C + ch];
-            s1 += partial[(size_t)(g + 32) * 2 * C + ch];
-            q1 += partial[(size_t)(g + 32) * 2 * C + C + ch];
-        }
-        if (g < G) {
-            s0 += partial[(size_t)g * 2 * C + ch];
-            q0 += partial[(size_t)g * 2 * C + C + ch];
+        for (int g0 = lane; g0 < G; g0 += 32 * BN_FIN_ILP) {
+            float sv[BN_FIN_ILP], qv[BN_FIN_ILP];
+#pragma unroll
+            for (int u = 0; u < BN_FIN_ILP; ++u) {
+                const int g = g0 + 32 * u;
+                const bool ok = g < G;
+                sv[u] = ok ? partial[(size_t)g * 2 * C + ch] : 0.f;
+                qv[u] = ok ? partial[(size_t)g * 2 * C + C + ch] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < BN_FIN_ILP; u += 2) {
+                s0 += sv[u]; q0 += qv[u];
+                s1 += sv[u + 1]; q1 += qv[u + 1];
+            }
         }
     }
     sm_s[lane][cl] = s0 + s1;

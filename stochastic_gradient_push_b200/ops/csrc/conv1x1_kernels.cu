@@ -531,7 +531,7 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 // statistics finalize: merge the R per-CTA rows (n, mean, M2) per channel (Chan et al.),
 // then the same outputs as bn_stats_finalize_kernel.  1024 threads = 32 row lanes x 32 channels.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
 c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt,
                          float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
@@ -546,10 +546,24 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     const bool live = ch < C;
     if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
 
-    // pass 1: total count and mean
+    // every row of this lane is loaded up front (R <= 148 -> at most 5 rows per lane per batch), so
+    // the kernel pays one L2 round trip instead of one per row
+    constexpr int ILP = 5;
     float n_sum = 0.f, m_sum = 0.f;
+    float nv[ILP], mv[ILP], qv[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+        const int r = lane + 32 * u;
+        const bool ok = live && r < R;
+        const int at = r * 3 * C + ch;                 // R * 3 * C < 2^20: 32-bit indexing
+        nv[u] = ok ? partial[at] : 0.f;
+        mv[u] = ok ? partial[at + C] : 0.f;
+        qv[u] = ok ? partial[at + 2 * C] : 0.f;
+        n_sum += nv[u];
+        m_sum = fmaf(nv[u], mv[u], m_sum);
+    }
     if (live)
-        for (int r = lane; r < R; r += 32) {
+        for (int r = lane + 32 * ILP; r < R; r += 32) {            // (only on parts with > 160 SMs)
             const float* p = partial + (size_t)r * 3 * C + ch;
             n_sum += p[0];
             m_sum = fmaf(p[0], p[C], m_sum);
@@ -559,6 +573,7 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     __syncthreads();
     if (lane == 0) {
         float n = 0.f, m = 0.f;
+#pragma unroll 4
         for (int l = 0; l < 32; ++l) { n += sm_a[l][cl]; m += sm_b[l][cl]; }
         sm_mu[cl] = (n > 0.f) ? m / n : 0.f;
         sm_a[0][cl] = n;
@@ -568,10 +583,15 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     const float n_tot = sm_a[0][cl];
     __syncthreads();
 
-    // pass 2: M2 = sum_p [ M2_p + n_p (mean_p - mu)^2 ]
+    // M2 = sum_p [ M2_p + n_p (mean_p - mu)^2 ]
     float m2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+        const float d = mv[u] - mu;
+        m2 += qv[u] + nv[u] * d * d;
+    }
     if (live)
-        for (int r = lane; r < R; r += 32) {
+        for (int r = lane + 32 * ILP; r < R; r += 32) {
             const float* p = partial + (size_t)r * 3 * C + ch;
             const float d = p[C] - mu;
             m2 += p[2 * (size_t)C] + p[0] * d * d;
@@ -580,6 +600,7 @@ c1_stats_finalize_kernel(const float* __restrict__ partial, int R, int C, const 
     __syncthreads();
     if (lane != 0 || !live) return;
     float tot = 0.f;
+#pragma unroll 4
     for (int l = 0; l < 32; ++l) tot += sm_b[l][cl];
     const float var = (n_tot > 0.f) ? tot / n_tot : 0.f;
     const float is = rsqrtf(var + eps);
