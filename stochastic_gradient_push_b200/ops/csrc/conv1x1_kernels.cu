@@ -711,11 +711,13 @@ cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorM
                    int M, int N, int K, float* partial, int mode, int grid, cudaStream_t st)
 {
     auto kern = mode == 1 ? c1_gemm_kernel<BN, 1> : (mode == 2 ? c1_gemm_kernel<BN, 2> : c1_gemm_kernel<BN, 0>);
-    static bool configured[3] = {false, false, false};
-    if (!configured[mode]) {
+    static bool configured[3][64] = {};            // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[mode][dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
-        configured[mode] = true;
+        if (dev >= 0 && dev < 64) configured[mode][dev] = true;
     }
     int smem = 0;
     const C1Plan plan = make_plan(BN, K, N / BN, mode == 2, smem);

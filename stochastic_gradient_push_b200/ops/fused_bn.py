@@ -16,6 +16,14 @@ and ``state_dict`` keys); ``forward(x, residual=None, relu=False)``.  Anything
 the kernels do not cover (CPU tensors, NCHW layout, C % 8 != 0, fp16/fp64)
 runs the reference composition ``relu(batch_norm(x) + residual)``, which is
 also the oracle in the numerics tests.
+
+``conv_bn_act`` / ``conv_bn_act_split`` go one step further for 1x1 / stride-1
+convolutions: the convolution itself runs as the hand-written tcgen05 GEMM of
+``csrc/conv1x1_kernels.cu`` (TMA operand ring, TMEM accumulators), whose
+epilogue produces the BatchNorm statistics (no separate statistics pass) and,
+in backward, adds the skip-branch gradient of a residual block inside the
+dgrad GEMM (no autograd accumulation pass).  Also here: the NHWC max-pool and
+the tensor-core stem convolution wrappers.
 """
 
 from __future__ import annotations
