@@ -23,6 +23,7 @@ graph) -- same kernel, the graph/mixing differ --, ``'osgp'`` (overlap), and
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Callable, Optional
 
 import torch
@@ -56,6 +57,9 @@ class GossipTrainer(object):
         self.static_loss = None
         self.static_out = None
         self._eager_steps = 0
+        # see _backward(); SGP_B200_BATCHED_GRAD_COPY=0 restores per-parameter accumulation
+        self.batched_grad_copy = os.environ.get('SGP_B200_BATCHED_GRAD_COPY', '1') != '0'
+        self._grad_slots = None
         # every launch of the step runs on ONE dedicated side stream: autograd's
         # AccumulateGrad nodes are then created on the stream the graph is captured on
         self.stream = torch.cuda.Stream(device=self.device)
@@ -77,6 +81,7 @@ class GossipTrainer(object):
 
     def _fwd_bwd(self):
         twin = getattr(self.model, '_twin', None)
+        net = None
         if twin:
             # bf16 twin: weights already live in bf16 (shadow arena), input buffer is bf16
             net = twin[0]
@@ -87,9 +92,39 @@ class GossipTrainer(object):
             with self._autocast():
                 out = self.model.module(self.static_in)
                 loss = self.criterion(out.float(), self.static_tgt)
-        loss.backward()
+        self._backward(loss, net if twin else self.model.module)
         self.static_loss.copy_(loss.detach())
         self.static_out = out.detach()
+
+    def _backward(self, loss, net):
+        """``loss.backward()`` without ~160 per-parameter accumulate kernels: the flat gradient
+        buffers are zero at this point (the fused SGD kernel clears them), so instead of letting
+        autograd run ``p.grad += g`` once per parameter, the ``.grad`` views are detached for
+        the backward pass (autograd then just keeps each fresh gradient) and the results are
+        written into the arena with one multi-tensor copy per dtype."""
+        if not self.batched_grad_copy:
+            loss.backward()
+            return
+        if self._grad_slots is None:
+            self._grad_slots = [(p, p.grad) for p in net.parameters()
+                                if p.requires_grad and p.grad is not None]
+        for p, _ in self._grad_slots:
+            p.grad = None
+        loss.backward()
+        by_dtype = {}
+        for p, view in self._grad_slots:
+            g = p.grad
+            p.grad = view
+            if g is None:
+                continue                                   # no gradient this step: slot stays zero
+            if g.dtype != view.dtype or g.shape != view.shape:
+                view.copy_(g)                              # foreign layout / dtype: plain copy
+                continue
+            dst, src = by_dtype.setdefault(view.dtype, ([], []))
+            dst.append(view)
+            src.append(g)
+        for dst, src in by_dtype.values():
+            torch._foreach_copy_(dst, src)
 
     def _step_sync(self):
         """forward/backward, then ONE kernel: SGD + publish + pull + mix + de-bias
