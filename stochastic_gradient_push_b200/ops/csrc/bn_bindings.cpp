@@ -255,6 +255,7 @@ static torch::Tensor stem_wgrad(torch::Tensor x, torch::Tensor dy)
 extern "C" {
 int c1_supported(long long M, int N, int K);
 int c1_partial_rows(long long M, int N, int num_sms);
+void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int* out);
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
                            const void* residual, int num_sms, cudaStream_t st);
 cudaError_t c1_launch_stats_finalize(const float* partial, int R, int C, const float* gamma, const float* beta,
@@ -283,6 +284,19 @@ static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
         return torch::empty({x.size(0), N, x.size(2), x.size(3)},
                             x.options().memory_format(at::MemoryFormat::ChannelsLast));
     return torch::empty({x.size(0), N}, x.options());
+}
+
+// host-side launch plan of the GEMM for a shape (no GPU needed)
+static py::dict conv1x1_plan(long long M, int N, int K, int num_sms, bool residual)
+{
+    TORCH_CHECK(c1_supported(M, N, K), "unsupported GEMM shape");
+    int v[7];
+    c1_describe_plan(M, N, K, num_sms, residual ? 1 : 0, v);
+    py::dict d;
+    d["block_n"] = v[0]; d["grid"] = v[1]; d["ctas_per_n"] = v[2]; d["stages"] = v[3];
+    d["resident_w"] = v[4] != 0; d["store_slabs"] = v[5]; d["smem_bytes"] = v[6];
+    d["partial_rows"] = c1_partial_rows(M, N, num_sms);
+    return d;
 }
 
 static int sm_count() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
@@ -363,6 +377,8 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
 void bind_bn(py::module& mod)
 {
     mod.def("conv1x1_can_fuse", &conv1x1_can_fuse);
+    mod.def("conv1x1_plan", &conv1x1_plan, py::arg("M"), py::arg("N"), py::arg("K"), py::arg("num_sms") = 148,
+            py::arg("residual") = false);
     mod.def("conv1x1_forward", &conv1x1_forward, py::arg("x"), py::arg("w"), py::arg("with_stats") = false,
             py::arg("residual") = py::none());
     mod.def("conv1x1_bn_forward", &conv1x1_bn_forward);

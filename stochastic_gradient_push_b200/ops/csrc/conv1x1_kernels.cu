@@ -736,6 +736,17 @@ int c1_supported(long long M, int N, int K)
     return M >= 1 && M < (1ll << 31) && N >= 64 && N % 64 == 0 && K >= 8 && K % 8 == 0;
 }
 
+// launch plan for a shape (host logic only; exercised by the CPU tests):
+// out = {BLOCK_N, grid, ctas_per_n, stages, resident, nbuf, dynamic smem bytes}
+void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int* out)
+{
+    int bn, per, grid, smem = 0;
+    grid_shape(M, N, num_sms, bn, per, grid);
+    const C1Plan p = make_plan(bn, K, N / bn, residual != 0, smem);
+    out[0] = bn; out[1] = grid; out[2] = per; out[3] = p.stages; out[4] = p.resident; out[5] = p.nbuf;
+    out[6] = smem;
+}
+
 // number of partial-statistics rows c1_launch_gemm writes for this shape
 int c1_partial_rows(long long M, int N, int num_sms)
 {
