@@ -98,6 +98,14 @@ class _PolledRecv(object):
         if self._err is not None:
             raise self._err
 
+    def wait_for(self, seconds: float) -> bool:
+        """Bounded wait: False when the message has not arrived within ``seconds``."""
+        if not self._done.wait(seconds):
+            return False
+        if self._err is not None:
+            raise self._err
+        return True
+
 
 class PeerMemoryTransport(object):
     """sm_100a data plane for STAND-ALONE gossipers (``README.md:67-68`` of the

@@ -153,11 +153,18 @@ class _C10dBackend(object):
             return True
         return all(_req_done(r) for r in self.pending[3])
 
-    def finish(self):
-        """Wait and fold: returns the residual push-sum weight."""
+    def finish(self, timeout_s: float = None):
+        """Wait and fold: returns the residual push-sum weight.  ``timeout_s`` is the
+        heartbeat: a peer that does not deliver in time raises ``NameError('Gossip flag
+        timeout')`` like the reference's gossip-flag wait (``gossip/distributed.py:349-352``)
+        instead of hanging until the process group's own (30 min) timeout."""
         reqs, recvs, _, _ = self.pending
-        for r in reqs:
-            r.wait()
+        # NCCL works keep their stream-ordered wait() (and NCCL's own watchdog); the heartbeat
+        # wrapper is for host-side (gloo) requests
+        host_side = self.comm_device.type == 'cpu'
+        deadline = time.time() + timeout_s if (timeout_s is not None and host_side) else None
+        for i in range(len(reqs)):
+            _wait_req(reqs, i, deadline)
         w_res = 0.0
         first = True
         for arena, bufs in recvs:
@@ -168,6 +175,25 @@ class _C10dBackend(object):
             first = False
         self.pending = None
         return w_res
+
+
+def _wait_req(reqs, i, deadline):
+    """``reqs[i].wait()`` bounded by the heartbeat deadline.  gloo offers no usable timed wait
+    (an expired ``Work.wait(timeout)`` closes the connection pair, and ``is_completed()`` never
+    flips), so an unfinished request is parked in a helper thread (:class:`_PolledRecv`) and the
+    wrapper replaces it in ``reqs`` -- a later retry waits on the same wrapper."""
+    req = reqs[i]
+    if deadline is None:
+        req.wait()
+        return
+    if not hasattr(req, 'wait_for'):
+        if _req_done(req):
+            req.wait()
+            return
+        from ..gossiper import _PolledRecv
+        req = reqs[i] = _PolledRecv(req)
+    if not req.wait_for(max(deadline - time.time(), 1e-3)):
+        raise NameError('Gossip flag timeout')
 
 
 def _req_done(req) -> bool:
@@ -592,7 +618,7 @@ class GossipDataParallel(Module):
         if non_blocking and not c.done():
             return False
         self.ps_numerator()
-        self._w += c.finish()
+        self._w += c.finish(self._timeout_s)
         self.params_mixed = True
         self.gossiping = False
         return True

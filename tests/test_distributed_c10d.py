@@ -271,3 +271,40 @@ def test_peers_per_itr_switch_mid_training_matches_simulation(overlap):
         got, w, _ = out[r]
         torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
         assert abs(w - ws[r]) < 1e-5
+
+
+def _heartbeat_worker(rank, world):
+    """Fault injection: rank 1 is 3 s late.  Rank 0's 1 s heartbeat must fire as the reference's
+    ``NameError('Gossip flag timeout')`` instead of hanging, and the exchange must
+    still be completable once the slow peer shows up (nothing was lost or double-counted)."""
+    import time
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    graph = sgp.RingGraph(rank, world)
+    model = GossipDataParallel(_model(rank), graph=graph, rank=rank, world_size=world,
+                               heartbeat_timeout=1.0)
+    before = _flat(model.module).clone()
+    if rank == 1:
+        time.sleep(3.0)
+    t0 = time.time()
+    model.transfer_params()
+    caught, waited = None, 0.0
+    try:
+        model.sync_comms()
+    except NameError as e:
+        caught, waited = str(e), time.time() - t0
+        assert model.gossiping and not model.params_mixed      # state intact: retry is possible
+        model._timeout_s = 60.0
+        model.sync_comms()
+    model.unbias()
+    return caught, waited, before.tolist(), _flat(model.module).tolist()
+
+
+def test_heartbeat_timeout_detects_a_slow_peer_and_recovers():
+    out = run_distributed(_heartbeat_worker, 2, timeout=120)
+    caught0, waited0, b0, a0 = out[0]
+    caught1, _, b1, a1 = out[1]
+    assert caught0 == 'Gossip flag timeout' and 0.9 <= waited0 < 2.5
+    assert caught1 is None
+    mean = [(x + y) / 2 for x, y in zip(b0, b1)]
+    assert torch.allclose(torch.tensor(a0), torch.tensor(mean), atol=1e-6)
+    assert torch.allclose(torch.tensor(a1), torch.tensor(mean), atol=1e-6)
