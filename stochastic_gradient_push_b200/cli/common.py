@@ -102,6 +102,10 @@ def build_parser(adpsgd: bool = False) -> argparse.ArgumentParser:
     p.add_argument('--num_classes', default=1000, type=int)
     p.add_argument('--image_size', default=224, type=int)
     p.add_argument('--device', default=None, help="'cuda' / 'cpu' (default: cuda if available)")
+    p.add_argument('--trace_file', default='', type=str,
+                   help='write a Chrome trace (PREFIX_r<rank>.json; NVTX ranges on CUDA) of the '
+                        'first --trace_iters training iterations')
+    p.add_argument('--trace_iters', default=50, type=int)
     return p
 
 

@@ -34,6 +34,7 @@ from .common import (CSVLog, Meter, accuracy, build_parser, finalize_args,
                      fresh_state, init_model, make_dataloader, update_learning_rate,
                      update_peers_per_itr, update_state)
 from ..experiment import ClusterManager, make_logger
+from ..utils import tracing
 
 
 def parse_args(argv=None):
@@ -112,6 +113,8 @@ def main(argv=None):
         torch.cuda.manual_seed(args.seed)
         torch.backends.cudnn.benchmark = True
 
+    if args.trace_file:
+        tracing.enable(args.trace_file, rank=args.rank)
     model, optimizer = build_model_and_optimizer(args, log)
     criterion = nn.CrossEntropyLoss()      # == KLDiv(log_softmax, one_hot) of the reference
     optimizer.zero_grad()
@@ -177,6 +180,8 @@ def main(argv=None):
         prec1 = validate(args, val_loader, model, criterion, log)
         log.info('Test accuracy: {}'.format(prec1))
     log.info('elapsed_time {0}'.format(time.time() - begin_time))
+    if tracing.get_tracer().enabled:            # shorter run than --trace_iters
+        log.info('trace written to %s' % tracing.disable().dump())
     if dist.is_initialized():
         dist.barrier()
     return state
@@ -201,11 +206,17 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
     for _ in range(itr):            # resume mid-epoch: skip what was already consumed
         next(it, None)
     t_batch = time.time()
+    traced = 0
     for i, (batch, target) in enumerate(it, start=itr):
+        if tracing.get_tracer().enabled:
+            traced += 1
+            if traced > args.trace_iters:       # bounded trace: dump once, then stop recording
+                log.info('trace written to %s' % tracing.disable().dump())
         target = target.to(dev, non_blocking=True)
         if dev == 'cuda' and not batch.is_cuda and args.all_reduce:
             batch = batch.to(dev, non_blocking=True)
         t_data = time.time() - t_batch
+        tracing.counter('data_ms', t_data * 1e3)
         t_nn = time.time()
         if i % 100 == 0:
             update_learning_rate(args, optimizer, epoch, itr=i, itr_per_epoch=len(loader))
@@ -213,18 +224,21 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
             # whole step = one CUDA-graph replay (forward+backward+fused gossip kernel);
             # the metrics are computed on the trainer's stream, before the next replay
             # can overwrite the static output buffers
-            trainer.step(batch, target)
+            with tracing.span('step[graph]', itr=i):
+                trainer.step(batch, target)
             with torch.cuda.stream(trainer.stream), torch.no_grad():
                 p1, p5 = accuracy(trainer.static_out, trainer.static_tgt, topk=(1, 5))
                 pending.append((torch.stack([trainer.static_loss.float().reshape(()),
                                              p1[0], p5[0]]), batch.size(0)))
         else:
-            with _autocast(args):
+            with tracing.span('forward', itr=i), _autocast(args):
                 output = model(batch)
                 loss = criterion(output.float(), target)
-            loss.backward()
-            optimizer.step()
-            optimizer.zero_grad()
+            with tracing.span('backward'):
+                loss.backward()
+            with tracing.span('optimizer'):
+                optimizer.step()
+                optimizer.zero_grad()
             if not args.overlap and not args.all_reduce:
                 model.transfer_params()
             with torch.no_grad():

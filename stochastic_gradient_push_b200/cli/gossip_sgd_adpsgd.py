@@ -29,6 +29,7 @@ import torch.nn as nn
 from .common import (CSVLog, Meter, accuracy, build_parser, finalize_args, fresh_state,
                      init_model, learning_rate_at, make_dataloader, update_state)
 from ..experiment import ClusterManager, make_logger
+from ..utils import tracing
 
 
 def parse_args(argv=None):
@@ -75,6 +76,8 @@ def main(argv=None):
         torch.cuda.manual_seed(args.seed)
         torch.backends.cudnn.benchmark = True
 
+    if args.trace_file:
+        tracing.enable(args.trace_file, rank=args.rank)
     net = init_model(args)
     model = BilatGossipDataParallel(
         net, master_addr=args.master_addr, master_port=str(args.master_port),
@@ -137,6 +140,8 @@ def main(argv=None):
         log.info('Test accuracy: {}'.format(prec1))
     model.disable_gossip()
     log.info('elapsed_time {0}'.format(time.time() - begin_time))
+    if tracing.get_tracer().enabled:
+        log.info('trace written to %s' % tracing.disable().dump())
     if dist.is_initialized():
         dist.barrier()
     model.shutdown()
@@ -158,12 +163,16 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
         target = target.to(dev, non_blocking=True)
         t_data = time.time() - t_batch
         t_nn = time.time()
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+        if tracing.get_tracer().enabled and i >= args.trace_iters:
+            log.info('trace written to %s' % tracing.disable().dump())
+        with tracing.span('forward', itr=i), torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
             output = model(batch)
             loss = criterion(output.float(), target)
-        loss.backward()          # end-of-backward hook: push grads, pull the gossip model
-        optimizer.step()         # local step on the train copy (overwritten by the next pull)
-        optimizer.zero_grad(set_to_none=False)
+        with tracing.span('backward+exchange'):
+            loss.backward()      # end-of-backward hook: push grads, pull the gossip model
+        with tracing.span('optimizer'):
+            optimizer.step()     # local step on the train copy (overwritten by the next pull)
+            optimizer.zero_grad(set_to_none=False)
         since_sync += 1
         # every 100 iterations, staggered by rank, publish progress and refresh the LR
         if (i + args.rank) % 100 == 0:

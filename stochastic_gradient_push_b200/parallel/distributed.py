@@ -48,6 +48,7 @@ from torch.nn.modules import Module
 from ..gossiper import C10dTransport
 from ..mixing_manager import UniformMixing
 from ..topology.graph_manager import NPeerDynamicDirectedExponentialGraph as NPDDEGraph
+from ..utils import tracing
 from ..utils.arena import FlatArena
 from ..utils.helpers import communicate, create_process_group, group_by_dtype, make_logger
 
@@ -223,6 +224,7 @@ class GossipDataParallel(Module):
         _INSTANCES[0] += 1
         self._instance_id = _INSTANCES[0]
         self._timeout_s = float(heartbeat_timeout)
+        self.exposed_comm_s = 0.0       # c10d data plane: host seconds blocked waiting for peers
 
         first_param = next(module.parameters())
         on_cuda = first_param.is_cuda
@@ -618,7 +620,12 @@ class GossipDataParallel(Module):
         if non_blocking and not c.done():
             return False
         self.ps_numerator()
-        self._w += c.finish(self._timeout_s)
+        t0 = time.time()
+        with tracing.span('gossip.wait+fold'):
+            self._w += c.finish(self._timeout_s)
+        # host time spent blocked on peers = communication NOT hidden behind compute
+        self.exposed_comm_s += time.time() - t0
+        tracing.counter('exposed_comm_ms', (time.time() - t0) * 1e3)
         self.params_mixed = True
         self.gossiping = False
         return True
@@ -632,11 +639,13 @@ class GossipDataParallel(Module):
             return False
 
         if self._kernel is not None:
-            self._launch_kernel_gossip()
+            with tracing.span('gossip.kernel'):
+                self._launch_kernel_gossip()
         else:
             self.ps_numerator()
             c = self._c10d
-            self_w = c.start(self._w, pollable=self.asynch)
+            with tracing.span('gossip.post'):
+                self_w = c.start(self._w, pollable=self.asynch)
             for arena in self._arenas.values():     # keep the self-loop share
                 arena.flat.mul_(self_w)
             self._w *= self_w

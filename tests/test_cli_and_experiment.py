@@ -163,6 +163,27 @@ def test_gossip_sgd_cli_two_ranks_cpu(tmp_path, master_port, extra):
         assert os.path.isfile(str(tmp_path / ('checkpoint_r%d_n2.pth.tar' % r)))
 
 
+def test_gossip_sgd_cli_writes_chrome_trace(tmp_path, master_port):
+    """--trace_file: per-rank Chrome trace with forward / backward / optimizer / gossip spans and
+    the exposed-communication counter, bounded by --trace_iters."""
+    import json
+    prefix = str(tmp_path / 'trace')
+    out = _torchrun(2, 'gossip_sgd.py', COMMON + [
+        '--graph_type', '5', '--fused', 'False', '--num_epochs', '1', '--train_fast', 'True',
+        '--checkpoint_dir', str(tmp_path) + '/', '--trace_file', prefix, '--trace_iters', '5'],
+        master_port)
+    assert out.returncode == 0, out.stdout[-3000:]
+    for r in range(2):
+        doc = json.load(open('%s_r%d.json' % (prefix, r)))
+        ev = doc['traceEvents']
+        spans = [e for e in ev if e.get('ph') == 'X']
+        names = {e['name'] for e in spans}
+        assert {'forward', 'backward', 'optimizer', 'gossip.post', 'gossip.wait+fold'} <= names, names
+        assert sum(e['name'] == 'forward' for e in spans) == 5            # bounded by --trace_iters
+        assert all(e['pid'] == r and e['dur'] >= 0 for e in spans)
+        assert any(e.get('ph') == 'C' and e['name'] == 'exposed_comm_ms' for e in ev)
+
+
 def test_gossip_sgd_cli_resume(tmp_path, master_port):
     base = COMMON + ['--graph_type', '5', '--checkpoint_dir', str(tmp_path) + '/']
     out = _torchrun(2, 'gossip_sgd.py', base + ['--num_epochs', '1'], master_port)
