@@ -29,7 +29,10 @@ def _flat(model):
 
 
 def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, nesterov,
-            ppi_switch=None):
+            ppi_switch=None, jitter_ms=0):
+    import random
+    import time
+    rng = random.Random(97 * rank + 5)
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
     from stochastic_gradient_push_b200.optim import FusedGossipSGD
     graph = getattr(sgp, graph_name)(rank, world, peers_per_itr=ppi)
@@ -46,10 +49,14 @@ def _worker(rank, world, graph_name, ppi, steps, push_sum, overlap, fused, neste
         if ppi_switch is not None and step == ppi_switch[0]:
             model.update_gossiper('peers_per_itr', ppi_switch[1])
         x, y = _batch(rank, step)
+        if jitter_ms:                    # randomised per-rank delays (SURVEY 5.2 stress test)
+            time.sleep(rng.uniform(0, jitter_ms) / 1e3)
         loss = ((model(x) - y) ** 2).mean()
         loss.backward()
         opt.step()
         opt.zero_grad()
+        if jitter_ms:
+            time.sleep(rng.uniform(0, jitter_ms) / 1e3)
         if not overlap:
             model.transfer_params()
     model.sync_comms()
@@ -132,6 +139,21 @@ def test_sync_gossip_matches_simulation(graph_name, ppi, push_sum, fused, nester
         got, w, is_num = out[r]
         torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
         assert abs(w - ws[r]) < 1e-5 and is_num is False
+
+
+@pytest.mark.parametrize('overlap', [False, True])
+def test_random_per_rank_delays_do_not_change_the_result(overlap):
+    """Race stress: ranks stall for random times before forward and before the
+    exchange; synchronous SGP and Overlap-SGP must still reproduce the deterministic simulation
+    bit-for-tolerance (no message applied twice, early or to the wrong step)."""
+    world, steps = 4, 8
+    name = 'NPeerDynamicDirectedExponentialGraph'
+    out = run_distributed(_worker, world, name, 1, steps, True, overlap, True, True, None, 30)
+    want, ws = _simulate(world, name, 1, steps, overlap, True)
+    for r in range(world):
+        got, w, _ = out[r]
+        torch.testing.assert_close(torch.tensor(got), want[r], rtol=1e-4, atol=1e-5)
+        assert abs(w - ws[r]) < 1e-5
 
 
 @pytest.mark.parametrize('fused', [False, True])
