@@ -99,5 +99,5 @@ def test_tiny_and_resnet18_train_step_cpu():
             loss = nn.functional.cross_entropy(net(x), torch.zeros(shape[0], dtype=torch.long))
             loss.backward()
             opt.step()
-            loss0 = loss0 if loss0 is not None else float(loss)
-        assert float(loss) < loss0
+            loss0 = loss0 if loss0 is not None else float(loss.detach())
+        assert float(loss.detach()) < loss0
