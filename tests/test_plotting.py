@@ -52,3 +52,26 @@ def test_parse_fairseq_log(tmp_path):
     assert list(df.index) == [2, 3]                   # epoch 1 skipped
     assert abs(df.loc[2, 'nll'] - 2.6) < 1e-9 and abs(df.loc[3, 'itr'] - 3000) < 1e-9
     assert abs(df.loc[2, 'time'] - 200.5) < 1e-9      # rank average of the max train_wall
+
+
+def test_trace_summary(tmp_path):
+    """`plotting.py trace`: per-span totals and the exposed-communication counter."""
+    from stochastic_gradient_push_b200.utils import tracing
+    import visualization.plotting as P
+    paths = []
+    for rank in range(2):
+        t = tracing.Tracer(str(tmp_path / 'tr'), rank=rank, enabled=True, nvtx=False)
+        for _ in range(3):
+            with t.span('forward'):
+                pass
+            with t.span('backward'):
+                pass
+            t.counter('exposed_comm_ms', 1.5)
+        paths.append(t.dump())
+    df = P.summarize_traces(paths)
+    assert set(df['rank']) == {0, 1}
+    fwd = df[(df['rank'] == 1) & (df['span'] == 'forward')].iloc[0]
+    assert fwd['calls'] == 3 and fwd['total_ms'] >= 0
+    exp = df[(df['rank'] == 0) & (df['span'] == '(exposed_comm counter)')].iloc[0]
+    assert exp['calls'] == 3 and abs(exp['total_ms'] - 4.5) < 1e-9
+    P.main(['trace'] + paths)          # CLI entry prints the table

@@ -10,6 +10,7 @@ paper, fairseq training logs (their training code is not part of either repo).
     python visualization/plotting.py scaling --dir results/ --algo SGP:SGP_IB_ --nodes 4 8 16 32
     python visualization/plotting.py curves  --dir results/ --algo SGP:SGP_ --algo AR:AR_ --nodes 8 16
     python visualization/plotting.py bench   SCALE_r01.json
+    python visualization/plotting.py trace   run_r0.json run_r1.json      (--trace_file output)
     python visualization/plotting.py transformer --log sgp=ps.out --log sgd=ar.out --world 8
 
 Unlike the reference (hard-coded experiment tags and an iterations-per-epoch
@@ -226,6 +227,33 @@ def plot_bench(json_paths: Sequence[str], save_fname='bench_scaling.pdf', headle
     return df
 
 
+def summarize_traces(json_paths: Sequence[str]):
+    """Per-rank span totals of the Chrome traces written by ``--trace_file`` (see
+    ``stochastic_gradient_push_b200/utils/tracing.py``): one row per (rank, span) with call
+    count, total / mean milliseconds and the share of the traced wall-clock, plus the summed
+    ``exposed_comm_ms`` counter (communication the step actually waited for)."""
+    rows = []
+    for p in json_paths:
+        with open(p) as f:
+            ev = json.load(f)['traceEvents']
+        spans = [e for e in ev if e.get('ph') == 'X']
+        if not spans:
+            continue
+        rank = spans[0]['pid']
+        wall = (max(e['ts'] + e['dur'] for e in spans) - min(e['ts'] for e in spans)) / 1e3
+        for name in sorted({e['name'] for e in spans}):
+            durs = [e['dur'] / 1e3 for e in spans if e['name'] == name]
+            rows.append({'rank': rank, 'span': name, 'calls': len(durs), 'total_ms': sum(durs),
+                         'mean_ms': sum(durs) / len(durs), 'share': sum(durs) / wall if wall else 0.0})
+        exposed = [e['args']['exposed_comm_ms'] for e in ev
+                   if e.get('ph') == 'C' and e.get('name') == 'exposed_comm_ms']
+        if exposed:
+            rows.append({'rank': rank, 'span': '(exposed_comm counter)', 'calls': len(exposed),
+                         'total_ms': sum(exposed), 'mean_ms': sum(exposed) / len(exposed),
+                         'share': sum(exposed) / wall if wall else 0.0})
+    return pd.DataFrame(rows, columns=['rank', 'span', 'calls', 'total_ms', 'mean_ms', 'share'])
+
+
 # --------------------------------------------------------------------------- #
 def _runs(specs, directory):
     out = []
@@ -249,6 +277,8 @@ def main(argv=None):
     p = sub.add_parser('bench')
     p.add_argument('json', nargs='+')
     p.add_argument('--out', default='bench_scaling.pdf')
+    p = sub.add_parser('trace')
+    p.add_argument('json', nargs='+', help='PREFIX_r<rank>.json files written by --trace_file')
     p = sub.add_parser('transformer')
     p.add_argument('--log', action='append', help='LABEL=PATH')
     p.add_argument('--world', type=int, default=8)
@@ -260,6 +290,8 @@ def main(argv=None):
         plot_itrs(_runs(a.algo, a.dir), a.nodes, a.out or 'itr.pdf', a.val)
     elif a.cmd == 'bench':
         print(plot_bench(a.json, a.out))
+    elif a.cmd == 'trace':
+        print(summarize_traces(a.json).to_string(index=False, float_format=lambda v: '%.3f' % v))
     else:
         plot_transformer(dict(s.split('=', 1) for s in a.log), a.world, a.out)
 
