@@ -1,5 +1,5 @@
-// 1x1 convolution (NHWC) as a tcgen05 GEMM with the BatchNorm statistics fused
-// into the epilogue -- sm_100a only.
+// 1x1 convolution (NHWC) as a tcgen05 GEMM with the BatchNorm statistics (forward) or the
+// skip-branch gradient accumulation (backward) fused into the epilogue -- sm_100a only.
 //
 //   Y[M, N] = X[M, K] . W[N, K]^T        M = batch*H*W, K = C_in, N = C_out, bf16 in / fp32 acc
 //
@@ -30,8 +30,16 @@
 // registers until the end: each epilogue warp keeps (n, K, sum(y-K), sum((y-K)^2)) with its
 // own shift K (its first output row), the eight warps are merged in shared memory into one
 // (n, mean, M2) row per CTA, and c1_stats_finalize_kernel merges the <= 148 rows with the
-// pairwise (Chan) update and emits mean / invstd / scale / shift and the running-statistics update, exactly what
-// bn_stats_finalize_kernel does for the stand-alone statistics pass.
+// pairwise (Chan) update and emits mean / invstd / scale / shift and the running-statistics
+// update, exactly what bn_stats_finalize_kernel does for the stand-alone statistics pass.
+//
+// Three epilogue modes share the producer / MMA pipeline:
+//   MODE 0  Y = X.W^T
+//   MODE 1  + the BatchNorm statistics above (forward of conv + BN: no separate statistics pass)
+//   MODE 2  Y = X.W^T + R, R's 4 KB slab prefetched by TMA one sub-tile ahead (own mbarrier per
+//           slab), summed in fp32 before the single bf16 rounding.  Used as the dgrad of the first
+//           convolution of a residual block with R = the skip-branch gradient, which replaces
+//           autograd's read-read-write accumulation pass over the block's widest tensor.
 //
 // Measured on B200 (benchmarks/conv1x1_bench.py, profiles/conv1x1_bench_*.log).
 //
