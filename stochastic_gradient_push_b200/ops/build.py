@@ -86,23 +86,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     cuda = _cuda_home()
     nvcc = os.path.join(cuda, 'bin', 'nvcc')
-    objs, log = [], []
-    for src in cu:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src) + '.o')
-        log.append(_run([nvcc] + NVCC_FLAGS + ['-I', CSRC, '-c', src, '-o', obj], verbose))
-        objs.append(obj)
-
     inc = ['-I' + p for p in ce.include_paths()] + [
         '-I' + os.path.join(cuda, 'include'), '-I' + CSRC,
         '-I' + sysconfig.get_paths()['include']]
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
     cxx = os.environ.get('CXX', 'g++')
+
+    # one compiler process per translation unit, all at once (the units are independent; the
+    # torch-header-heavy bindings dominate, so the wall-clock is ~ the slowest unit)
+    jobs = []
+    for src in cu:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src) + '.o')
+        jobs.append((obj, [nvcc] + NVCC_FLAGS + ['-I', CSRC, '-c', src, '-o', obj]))
     for src in cpp:
         obj = os.path.join(OBJ_DIR, os.path.basename(src) + '.o')
-        _run([cxx, '-O2', '-std=c++17', '-fPIC', '-DTORCH_EXTENSION_NAME=' + EXT_NAME,
-              '-DTORCH_API_INCLUDE_EXTENSION_H', '-D_GLIBCXX_USE_CXX11_ABI=%d' % abi,
-              '-Wno-deprecated-declarations'] + inc + ['-c', src, '-o', obj], verbose)
-        objs.append(obj)
+        jobs.append((obj, [cxx, '-O2', '-std=c++17', '-fPIC', '-DTORCH_EXTENSION_NAME=' + EXT_NAME,
+                           '-DTORCH_API_INCLUDE_EXTENSION_H', '-D_GLIBCXX_USE_CXX11_ABI=%d' % abi,
+                           '-Wno-deprecated-declarations'] + inc + ['-c', src, '-o', obj]))
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, min(len(jobs), os.cpu_count() or 1, int(os.environ.get('SGP_B200_BUILD_JOBS', '8'))))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        outs = list(pool.map(lambda job: _run(job[1], verbose), jobs))    # re-raises the first failure
+    objs = [obj for obj, _ in jobs]
+    log = outs[:len(cu)]                                                  # ptxas -v output of the kernels
 
     torch_lib = os.path.join(os.path.dirname(torch.__file__), 'lib')
     link = [cxx, '-shared', '-o', out] + objs + [
