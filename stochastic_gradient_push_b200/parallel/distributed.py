@@ -38,7 +38,7 @@ numerator / de-biased alternation.
 from __future__ import annotations
 
 import time
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 import torch.distributed as dist
