@@ -11,14 +11,18 @@ N > 1 is launched by the driver as
 (one rank per GPU; RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* come from the env).
 
 What is timed (our arm):
-  * `value`  : K replays of the captured training step -- forward (bf16 autocast,
-    NHWC) + loss + backward + ONE fused sm_100a kernel (SGD-momentum + push-sum
-    publish + P2P pull over NVLink + mix + de-bias) -- inputs resident on the
-    device, CUDA events on the launching stream, barrier + synchronize on both
-    sides, max over ranks.  Whole-job images/s.
-  * `e2e`    : the same K steps through the public API (`GossipTrainer.step`) with
-    the step's inputs copied from pinned host memory every step (prefetch stream)
-    and the step's loss copied back to pinned host memory every step.
+  * `value`  : K replays of the captured training step -- forward + fused softmax-xent /
+    prec@1 / prec@5 + backward + ONE fused sm_100a kernel (SGD-momentum + push-sum publish +
+    P2P pull over NVLink + mix + de-bias) -- inputs resident on the device, CUDA events on
+    the launching stream, barrier + synchronize on both sides, max over ranks.  Whole-job
+    images/s.  Default precision = the reference arm's: fp32 activations / weights / master
+    parameters with TF32 tensor-core convolution math (`--dtype fp32`).
+  * `e2e`    : the same K steps through the public API (`GossipTrainer.step`) with the
+    step's inputs copied from pinned host memory every step (prefetch stream) and the
+    step's results (loss, prec@1, prec@5 = 12 bytes, what the reference loop reads back
+    with three `.item()` calls) copied to pinned host memory every step.
+  * `secondary`: the same two numbers for bf16 compute at the same batch and for the
+    reference's per-GPU batch of 32, clearly labelled (never the headline).
 Synthetic 3x224x224 fp32 images, random-init ResNet-50 (no network / datasets).
 """
 
@@ -46,7 +50,11 @@ def parse():
                     help='per-agent batch; 256 = every shipped job script of the reference '
                          '(job_scripts/submit_*.sh: --batch_size 256 per gossip agent); one agent '
                          'per B200 here')
-    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--dtype', default='fp32', choices=['bf16', 'fp32'],
+                    help='fp32 (default): fp32 activations / weights with TF32 tensor-core convolutions, '
+                         'the precision of the reference arm; bf16: reported as a labelled secondary line')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the secondary (other precision / per-GPU batch 32) measurements')
     ap.add_argument('--model', default='resnet50')
     ap.add_argument('--ppi', type=int, default=1)
     ap.add_argument('--no-graph', action='store_true')
@@ -115,73 +123,51 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- #
-def run_ours(args):
+def _build(args, dtype, bs, rank, world, dev):
+    """model + trainer for one measured configuration"""
     import torch
-    import torch.distributed as dist
-    sys.path.insert(0, ROOT)
     import stochastic_gradient_push_b200 as sgp
     from stochastic_gradient_push_b200 import models
     from stochastic_gradient_push_b200.optim import FusedGossipSGD
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
     from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
 
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
-        dist.barrier()
-    torch.backends.cudnn.benchmark = True
+    amp = torch.bfloat16 if dtype == 'bf16' else None
     torch.manual_seed(1 + rank)
-
-    bs, K, W = args.batch_size, args.steps, args.warmup
-    amp = torch.bfloat16 if args.dtype == 'bf16' else None
     net = models.MODEL_ZOO[args.model]()
     models.init_imagenet_in_1hr(net)
     net = net.to(dev).to(memory_format=torch.channels_last)
-
-    if args.algo == 'adpsgd':
-        return run_adpsgd(args, net, rank, world, dev, amp)
+    lr = 0.1 * bs * world / 256
     if args.algo == 'ar':
         from stochastic_gradient_push_b200.parallel.allreduce import AllReduceDataParallel, ARTrainer
         model = AllReduceDataParallel(net)
-        trainer = ARTrainer(model, lr=0.1 * bs * world / 256, momentum=0.9, weight_decay=1e-4,
-                            nesterov=True, amp_dtype=amp, use_cuda_graph=not args.no_graph)
-        kernels_per_step = 1
-        graph_name = 'all-reduce'
+        trainer = ARTrainer(model, lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True,
+                            amp_dtype=amp, use_cuda_graph=not args.no_graph)
+        return net, model, trainer, 'all-reduce'
+    if args.algo == 'dpsgd':
+        graph = sgp.RingGraph(rank, world, peers_per_itr=args.ppi)
+        graph_name = 'static ring'
     else:
-        if args.algo == 'dpsgd':
-            graph = sgp.RingGraph(rank, world, peers_per_itr=args.ppi)
-            graph_name = 'static ring'
-        else:
-            graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world, peers_per_itr=args.ppi)
-            graph_name = 'n-peer dynamic directed exponential'
-        model = GossipDataParallel(net, graph=graph, push_sum=(args.algo != 'dpsgd'),
-                                   overlap=(args.algo == 'osgp'), rank=rank, world_size=world,
-                                   verbose=False, heartbeat_timeout=60,
-                                   compute_dtype=(torch.bfloat16 if (amp is not None and not args.autocast)
-                                                  else None))
-        opt = FusedGossipSGD(model, lr=0.1 * bs * world / 256, momentum=0.9,
-                             weight_decay=1e-4, nesterov=True)
-        trainer = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=not args.no_graph)
-        kernels_per_step = 2 if (args.algo == 'osgp' and world > 1) else 1
-    # our own sm_100a kernels per training step: 6 per fused BatchNorm (stats, finalize,
-    # apply | reduce, finalize, dx), 2 per NHWC max-pool, plus the gossip kernel(s)
-    from stochastic_gradient_push_b200.ops.fused_bn import FusedBatchNormAct2d, MaxPool2dNHWC
-    n_bn = sum(isinstance(m, FusedBatchNormAct2d) for m in net.modules())
-    n_pool = sum(isinstance(m, MaxPool2dNHWC) for m in net.modules())
-    kernels_per_step += 6 * n_bn + 2 * n_pool
-    # (for 1x1 convolutions the "stats" launch is the tcgen05 GEMM whose epilogue produces them);
-    # + stem convolution forward / wgrad, + one dgrad GEMM (skip gradient folded in) per bottleneck
-    from stochastic_gradient_push_b200.ops import fused_bn as _fb
-    from stochastic_gradient_push_b200.models.resnet import Bottleneck
-    kernels_per_step += 2
-    if _fb.USE_TCGEN05_CONV1X1:
-        kernels_per_step += sum(isinstance(m, Bottleneck) for m in net.modules())
+        graph = sgp.NPeerDynamicDirectedExponentialGraph(rank, world, peers_per_itr=args.ppi)
+        graph_name = 'n-peer dynamic directed exponential'
+    model = GossipDataParallel(net, graph=graph, push_sum=(args.algo != 'dpsgd'),
+                               overlap=(args.algo == 'osgp'), rank=rank, world_size=world,
+                               verbose=False, heartbeat_timeout=60,
+                               compute_dtype=(torch.bfloat16 if (amp is not None and not args.autocast)
+                                              else None))
+    opt = FusedGossipSGD(model, lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    trainer = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=not args.no_graph)
+    return net, model, trainer, graph_name
 
+
+def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
+    """One configuration: W warm-up steps, K device-timed replays (`value`), then K steps through
+    the public API with H2D of the inputs and D2H of [loss, prec@1, prec@5] every step (`e2e`)."""
+    import torch
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.ops import native
+
+    net, model, trainer, graph_name = _build(args, dtype, bs, rank, world, dev)
     # synthetic data: a small pool of pinned host batches (the loader's output)
     g = torch.Generator().manual_seed(1234 + rank)
     pool = [(torch.randn(bs, 3, 224, 224, generator=g).pin_memory(),
@@ -198,9 +184,10 @@ def run_ours(args):
     for i in range(max(W, 5)):
         trainer.step(*pool[i % len(pool)])
     sync_all()
+    launches_per_step = trainer.own_launches_per_step
 
     # ---- device-only timed region -------------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
@@ -230,36 +217,103 @@ def run_ours(args):
             slots.append(trainer.step(None, None, nxt[0], nxt[1]))
         e1.record(trainer.stream)
         sync_all()
-        losses = [float(trainer.loss_ring[s]) for s in slots]     # D2H results, all K read
+        rows = [trainer.metrics_ring[s].tolist() for s in slots]      # D2H results, all K read
         ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         ms2 = ms2.item()
         e2e = {'value': round(bs * world * K / (ms2 / 1e3), 2), 'unit': 'images/s',
                'ms_per_step': round(ms2 / K, 4),
-               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
-               'last_loss': round(losses[-1], 4)}
+               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 12,
+               'per_step_results': 'loss, prec@1, prec@5 (as the reference loop, gossip_sgd.py:394-407)',
+               'last_loss': round(rows[-1][0], 4), 'last_prec1': round(rows[-1][1], 3),
+               'last_prec5': round(rows[-1][2], 3)}
     trainer.finish()
+    res = {'value': round(value, 2), 'ms_per_step': round(ms / K, 4), 'e2e': e2e, 'clocks': clocks,
+           'launches_per_step': launches_per_step, 'graph_name': graph_name,
+           'native_ops': native.describe_paths() if hasattr(native, 'describe_paths') else None}
+    del trainer, model, net, pool
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+DTYPE_LABEL = {'fp32': 'fp32 (fp32 activations/weights/master, TF32 tensor-core conv math = the '
+                       "reference's cuDNN default)",
+               'bf16': 'bf16 (bf16 NHWC activations + conv math, fp32 master weights / BN / gossip)'}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from stochastic_gradient_push_b200 import models
+    from stochastic_gradient_push_b200.ops import fused_bn as _fb
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+        dist.barrier()
+    torch.backends.cudnn.benchmark = True
+    # the reference's defaults: TF32 inside cuDNN convolutions, full fp32 for matmul (the classifier)
+    torch.backends.cudnn.allow_tf32 = True
+
+    bs, K, W = args.batch_size, args.steps, args.warmup
+    if args.algo == 'adpsgd':
+        amp = torch.bfloat16 if args.dtype == 'bf16' else None
+        torch.manual_seed(1 + rank)
+        net = models.MODEL_ZOO[args.model]()
+        models.init_imagenet_in_1hr(net)
+        net = net.to(dev).to(memory_format=torch.channels_last)
+        return run_adpsgd(args, net, rank, world, dev, amp)
+
+    main = measure(args, args.dtype, bs, K, W, rank, world, dev, sample_clocks=True)
+    # secondary, clearly labelled lines: the other precision at the headline batch, and the
+    # reference's per-GPU batch (32 images per GPU in its 8-GPU-per-node job scripts), where the
+    # gossip step is a larger share of the iteration
+    secondary = {}
+    if not args.no_secondary:
+        other = 'bf16' if args.dtype == 'fp32' else 'fp32'
+        for key, (dt, b) in (('%s_bs%d' % (other, bs), (other, bs)), ('%s_bs32' % args.dtype, (args.dtype, 32))):
+            if (dt, b) == (args.dtype, bs):
+                continue
+            r = measure(args, dt, b, K, W, rank, world, dev, sample_clocks=False)
+            secondary[key] = {'dtype': DTYPE_LABEL[dt], 'per_gpu_batch': b, 'value': r['value'],
+                              'unit': 'images/s', 'ms_per_step': r['ms_per_step'],
+                              'e2e_value': r['e2e']['value'] if r['e2e'] else None,
+                              'e2e_ms_per_step': r['e2e']['ms_per_step'] if r['e2e'] else None}
 
     if rank == 0:
         out = {
-            'metric': 'resnet50_%s_images_per_sec' % args.algo, 'value': round(value, 2),
+            'metric': 'resnet50_%s_images_per_sec' % args.algo, 'value': main['value'],
             'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': round(ms / K, 4), 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic', 'impl': 'ours',
-            'config': {'model': args.model, 'algorithm': args.algo, 'graph': graph_name,
+            'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': DTYPE_LABEL[args.dtype], 'data': 'synthetic', 'impl': 'ours',
+            'config': {'model': args.model, 'algorithm': args.algo, 'graph': main['graph_name'],
                        'peers_per_itr': args.ppi, 'per_gpu_batch': bs, 'global_batch': bs * world,
                        'image': '3x224x224', 'parallelism': 'dp%d-gossip' % world,
                        'master_weights': 'fp32 flat arena', 'layout': 'NHWC',
-                       'bf16_path': ('autocast' if (args.autocast or args.algo == 'ar') else
-                                     'shadow weights written by the gossip kernel'),
+                       'compute_path': ('fp32 activations and weights; TF32 tcgen05 / cuDNN convolutions'
+                                        if args.dtype == 'fp32' else
+                                        ('autocast' if (args.autocast or args.algo == 'ar') else
+                                         'bf16 shadow weights written by the gossip kernel')),
                        'cuda_graph': not args.no_graph,
-                       'conv1x1': ('tcgen05 GEMM (TMA/TMEM), BN statistics and skip gradient fused '
-                                   'into its epilogues' if _fb.USE_TCGEN05_CONV1X1 else 'library'),
+                       'conv1x1': ('tcgen05 GEMM (TMA/TMEM, kind::%s), BN statistics and skip gradient '
+                                   'fused into its epilogues' % ('tf32' if args.dtype == 'fp32' else 'f16')
+                                   if _fb.USE_TCGEN05_CONV1X1 else 'library'),
+                       'loss': 'fused softmax-xent + prec@1/5 kernel inside the captured step',
                        'l2': 'per-step working set (activations+weights > 1 GB) exceeds the '
                              '126 MB L2; no explicit flush'},
-            'clocks': clocks, 'e2e': e2e,
-            'gpu_launches': kernels_per_step * K,
+            'clocks': main['clocks'], 'e2e': main['e2e'],
+            'gpu_launches': (main['launches_per_step'] or 0) * K,
+            'gpu_launches_per_step': main['launches_per_step'],
+            'secondary': secondary,
         }
         print(json.dumps(out))
     if world > 1:

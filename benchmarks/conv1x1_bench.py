@@ -58,16 +58,20 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--iters', type=int, default=15)
     ap.add_argument('--out', default='')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'],
+                    help='fp32: fp32 operands, TF32 tensor-core math (kind::tf32) vs cuDNN TF32')
     args = ap.parse_args()
+    DT = torch.float32 if args.dtype == 'fp32' else torch.bfloat16
+    esz = 4.0 if args.dtype == 'fp32' else 2.0
     native.load()
     flush = torch.zeros(64 * 1024 * 1024, device='cuda')          # 256 MB > L2
     rows, tot_lib, tot_tc = [], 0.0, 0.0
     for hw, cin, cout, add, mult in LAYERS:
-        conv = nn.Conv2d(cin, cout, 1, bias=False).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        conv = nn.Conv2d(cin, cout, 1, bias=False).cuda().to(DT).to(memory_format=torch.channels_last)
         bn = FusedBatchNormAct2d(cout).cuda()
-        x = torch.randn(args.batch, cin, hw, hw, device='cuda').to(torch.bfloat16) \
+        x = torch.randn(args.batch, cin, hw, hw, device='cuda').to(DT) \
             .contiguous(memory_format=torch.channels_last)
-        res = torch.randn(args.batch, cout, hw, hw, device='cuda').to(torch.bfloat16) \
+        res = torch.randn(args.batch, cout, hw, hw, device='cuda').to(DT) \
             .contiguous(memory_format=torch.channels_last) if add else None
         w = conv.weight.detach()
         C = native.load()
@@ -83,7 +87,7 @@ def main():
             out['tc_gemm_only'] = timed(lambda: C.conv1x1_forward(x, w), args.iters, flush)
             out['tc_gemm_stats'] = timed(lambda: C.conv1x1_forward(x, w, True), args.iters, flush)
         M = args.batch * hw * hw
-        gemm_bytes = 2.0 * (M * cin + M * cout + cin * cout)
+        gemm_bytes = esz * (M * cin + M * cout + cin * cout)
         rows.append(dict(hw=hw, cin=cin, cout=cout, add=add, mult=mult, M=M,
                          gemm_tbps=gemm_bytes / out['tc_gemm_only'] / 1e9,
                          lib_conv_tbps=gemm_bytes / out['lib_conv_only'] / 1e9, **out))
@@ -98,12 +102,12 @@ def main():
     # backward of the first 1x1 convolution of every bottleneck: dX = dY . W (+ skip gradient)
     drows, d_lib, d_tc = [], 0.0, 0.0
     for hw, width, cin, mult in DGRAD_LAYERS:
-        dy = torch.randn(args.batch, width, hw, hw, device='cuda').to(torch.bfloat16) \
+        dy = torch.randn(args.batch, width, hw, hw, device='cuda').to(DT) \
             .contiguous(memory_format=torch.channels_last)
-        skip = torch.randn(args.batch, cin, hw, hw, device='cuda').to(torch.bfloat16) \
+        skip = torch.randn(args.batch, cin, hw, hw, device='cuda').to(DT) \
             .contiguous(memory_format=torch.channels_last)
         xin = torch.empty_like(skip)
-        w = (torch.randn(width, cin, 1, 1, device='cuda') * cin ** -0.5).to(torch.bfloat16)
+        w = (torch.randn(width, cin, 1, 1, device='cuda') * cin ** -0.5).to(DT)
         C = native.load()
 
         def lib():
@@ -128,7 +132,7 @@ def main():
     if args.out:
         os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
         with open(args.out, 'w') as f:
-            json.dump(dict(batch=args.batch, total_library_ms=tot_lib, total_tcgen05_ms=tot_tc, layers=rows,
+            json.dump(dict(batch=args.batch, dtype=args.dtype, total_library_ms=tot_lib, total_tcgen05_ms=tot_tc, layers=rows,
                            dgrad_library_ms=d_lib, dgrad_tcgen05_ms=d_tc, dgrad_layers=drows), f, indent=1)
 
 

@@ -9,8 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stochastic_gradient_push_b200.ops.fused_bn import fused_bn_act, MaxPool2dNHWC   # noqa: E402
 
 dev = 'cuda'
+DT = torch.float32 if '--fp32' in sys.argv else torch.bfloat16
 N, C, H, W = 256, 256, 56, 56
-x = torch.randn(N, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+x = torch.randn(N, C, H, W, device=dev).to(DT).contiguous(memory_format=torch.channels_last)
 res = torch.randn_like(x)
 w = torch.ones(C, device=dev, requires_grad=True)
 b = torch.zeros(C, device=dev, requires_grad=True)
@@ -19,7 +20,7 @@ xs = x.clone().requires_grad_(True)
 rs = res.clone().requires_grad_(True)
 dy = torch.randn_like(x)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-bytes_t = x.numel() * 2
+bytes_t = x.numel() * x.element_size()
 
 
 def timed(fn, iters=10):
@@ -57,7 +58,7 @@ print('BN+ReLU      fwd %.3f ms (3 passes -> %.2f TB/s)   bwd %.3f ms (5 passes 
 print('BN+add+ReLU  fwd %.3f ms (4 passes -> %.2f TB/s)   bwd %.3f ms (7 passes -> %.2f TB/s)'
       % (t_fa, 4 * gb / t_fa / 1e3, t_ba, 7 * gb / t_ba / 1e3))
 
-xp = torch.randn(256, 64, 112, 112, device=dev).bfloat16().contiguous(
+xp = torch.randn(256, 64, 112, 112, device=dev).to(DT).contiguous(
     memory_format=torch.channels_last).requires_grad_(True)
 mp = MaxPool2dNHWC(3, 2, 1)
 yp = mp(xp)

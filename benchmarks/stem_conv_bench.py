@@ -13,8 +13,9 @@ torch.backends.cudnn.benchmark = True
 C = native.load()
 dev = 'cuda'
 B = 256
-x = torch.randn(B, 3, 224, 224, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-w = torch.randn(64, 3, 7, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+DT = torch.float32 if '--fp32' in sys.argv else torch.bfloat16     # fp32: TF32 mma.sync kernels vs cuDNN TF32
+x = torch.randn(B, 3, 224, 224, device=dev).to(DT).contiguous(memory_format=torch.channels_last)
+w = torch.randn(64, 3, 7, 7, device=dev).to(DT).contiguous(memory_format=torch.channels_last)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -41,6 +42,6 @@ t_cudnn_w = timed(lambda: torch.ops.aten.convolution_backward(
     dy, x, w, None, [2, 2], [3, 3], [1, 1], False, [0, 0], 1, [False, True, False]))
 t_ours_f = timed(lambda: C.stem_forward(x, w))
 t_ours_b = timed(lambda: C.stem_wgrad(x, dy))
-io = (x.numel() + y.numel()) * 2 / 1e6
+io = (x.numel() + y.numel()) * x.element_size() / 1e6
 print('stem conv batch %d: cuDNN fwd %.3f ms, wgrad-only %.3f ms, fwd+wgrad %.3f ms | ours fwd %.3f ms (%.2f TB/s), wgrad %.3f ms'
       % (B, t_cudnn_f, t_cudnn_w, t_cudnn_fb, t_ours_f, io / t_ours_f / 1e3, t_ours_b))

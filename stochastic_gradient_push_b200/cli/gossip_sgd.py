@@ -121,7 +121,9 @@ def main(argv=None):
     args._trainer = None
     if args.cuda_graph and not args.all_reduce and args.fused and getattr(model, '_kernel', None):
         from ..parallel.trainer import GossipTrainer
-        args._trainer = GossipTrainer(model, optimizer, criterion,
+        # criterion=None: the trainer's fused softmax-xent + prec@1/5 kernel (same value as
+        # nn.CrossEntropyLoss; tests/test_fused_loss_gpu.py)
+        args._trainer = GossipTrainer(model, optimizer, None,
                                       amp_dtype=torch.bfloat16 if args.amp else None)
 
     state = fresh_state(model.state_dict(), optimizer.state_dict())
@@ -191,6 +193,18 @@ def _autocast(args):
     return torch.autocast('cuda', dtype=torch.bfloat16, enabled=bool(args.amp and args.device == 'cuda'))
 
 
+def _drain_metrics(trainer, pending):
+    """[loss, prec@1, prec@5] of every pending iteration with one synchronisation.  Graph path:
+    the rows already sit in the trainer's pinned ring (slots); eager path: device tensors.
+    Also the place where the gossip kernels' health word is polled (a peer that stopped
+    publishing raises here, like the reference's 'Gossip flag timeout')."""
+    if trainer is not None:
+        trainer.stream.synchronize()
+        trainer.check()
+        return [trainer.metrics_ring[slot].tolist() for slot, _ in pending]
+    return torch.stack([v for v, _ in pending]).cpu().tolist()
+
+
 def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, loader, epoch,
           itr, csv, log):
     losses, top1, top5 = Meter(ptag='Loss'), Meter(ptag='Prec@1'), Meter(ptag='Prec@5')
@@ -224,12 +238,11 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
             # whole step = one CUDA-graph replay (forward+backward+fused gossip kernel);
             # the metrics are computed on the trainer's stream, before the next replay
             # can overwrite the static output buffers
+            # (loss, prec@1, prec@5 come out of the fused loss kernel inside the graph and land
+            # in the trainer's pinned metrics ring: 12 bytes per step, no host sync)
             with tracing.span('step[graph]', itr=i):
-                trainer.step(batch, target)
-            with torch.cuda.stream(trainer.stream), torch.no_grad():
-                p1, p5 = accuracy(trainer.static_out, trainer.static_tgt, topk=(1, 5))
-                pending.append((torch.stack([trainer.static_loss.float().reshape(()),
-                                             p1[0], p5[0]]), batch.size(0)))
+                slot = trainer.step(batch, target)
+            pending.append((slot, batch.size(0)))
         else:
             with tracing.span('forward', itr=i), _autocast(args):
                 output = model(batch)
@@ -255,11 +268,9 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
         t_batch = time.time()
 
         last = (limit not in (None, -1) and i + 1 == limit)
-        if i % args.print_freq == 0 or last:
-            if trainer is not None:
-                trainer.stream.synchronize()
-            vals = torch.stack([v for v, _ in pending]).cpu()      # ONE sync per interval
-            for (l, a1, a5), (_, n) in zip(vals.tolist(), pending):
+        if i % args.print_freq == 0 or last or len(pending) >= 512:
+            vals = _drain_metrics(trainer, pending)                # ONE sync per interval
+            for (l, a1, a5), (_, n) in zip(vals, pending):
                 losses.update(l, n)
                 top1.update(a1, n)
                 top5.update(a5, n)
@@ -268,10 +279,12 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
         if last:
             break
     if trainer is not None:
-        torch.cuda.synchronize()       # eval / checkpointing run on the default stream
+        # end of epoch: land the deferred SGD / gathered residual (overlap) so that validation
+        # and state_dict() see every update; eval / checkpointing run on the default stream
+        trainer.finish()
     if pending:
-        vals = torch.stack([v for v, _ in pending]).cpu()
-        for (l, a1, a5), (_, n) in zip(vals.tolist(), pending):
+        vals = _drain_metrics(trainer, pending)
+        for (l, a1, a5), (_, n) in zip(vals, pending):
             losses.update(l, n)
             top1.update(a1, n)
             top5.update(a5, n)

@@ -12,6 +12,8 @@
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -21,8 +23,14 @@
 
 namespace py = pybind11;
 
+// every kernel of this extension is launched through one of the two CHECK macros; they count
+// the launches (expressions that call a *_launch_* entry point) so that bench.py can report how
+// many of OUR kernels one captured training step contains (`launch_count()` delta over a capture)
+std::atomic<long long> g_sgp_kernel_launches{0};
+
 #define SGP_CUDA_CHECK(expr)                                                        \
     do {                                                                            \
+        if (std::strstr(#expr, "_launch_") != nullptr) ++g_sgp_kernel_launches;     \
         cudaError_t _e = (expr);                                                    \
         if (_e != cudaSuccess)                                                      \
             throw std::runtime_error(std::string(#expr) + " failed: " +             \
@@ -164,6 +172,13 @@ public:
         keep_.push_back(state);
         keep_.push_back(hyper);
         max_grid_ = sgp_max_resident_ctas(device_);
+        // the warp-specialised TMA step kernel (default for the full SGP / D-PSGD step) is bound by
+        // its dynamic shared memory; the grid has to be co-resident for BOTH kernels because the
+        // ranks of a job may mix them (flags are matched by CTA index)
+        const int pipe_grid = sgp_max_resident_ctas_pipe(device_);
+        if (pipe_grid > 0 && (max_grid_ == 0 || pipe_grid < max_grid_)) max_grid_ = pipe_grid;
+        const char* env = std::getenv("SGP_B200_PIPE");
+        use_pipe_ = !(env && env[0] == '0');
         args_.segments = 4;
     }
 
@@ -216,8 +231,16 @@ public:
         if (a.flags & SGP_F_PUBLISH) TORCH_CHECK(a.outboxes, "publish needs outboxes");
         if (a.flags & SGP_F_PHASE2) TORCH_CHECK(a.flags & SGP_F_PUBLISH, "phase 2 needs publish");
         c10::cuda::CUDAGuard guard(device_);
-        SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
+        const unsigned int full = SGP_F_PHASE1 | SGP_F_PUBLISH | SGP_F_PHASE2;
+        const unsigned int not_piped = SGP_F_FOLD_RES | SGP_F_NO_ROTATE | SGP_F_KEEP_Z | SGP_F_SELF_FROM_Z;
+        if (use_pipe_ && (a.flags & full) == full && (a.flags & not_piped) == 0)
+            SGP_CUDA_CHECK(sgp_launch_step_pipe(&a, grid, at::cuda::getCurrentCUDAStream()));
+        else
+            SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
     }
+
+    void set_pipe(bool on) { use_pipe_ = on; }
+    bool pipe() const { return use_pipe_; }
 
     void gather(int grid, int pub_grid, bool tma)
     {
@@ -288,6 +311,7 @@ private:
     int device_ = 0;
     int max_grid_ = 0;
     bool grad_bf16_ = false;
+    bool use_pipe_ = true;
     std::vector<torch::Tensor> keep_;
     std::vector<torch::Tensor> sched_keep_;
     torch::Tensor grad_keep_;
@@ -331,6 +355,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
     mod.def("scale_", &scale_, py::arg("x"), py::arg("scalar"), py::arg("invert"),
             py::arg("shadow") = py::none());
     mod.def("zero_", &zero_);
+    mod.def("launch_count", []() { return (long long)g_sgp_kernel_launches.load(); },
+            "kernels of this extension launched (or captured) so far by this process");
     mod.def("max_resident_ctas", &sgp_max_resident_ctas);
 
     mod.attr("CHUNK") = (int)SGP_CHUNK;
@@ -376,6 +402,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("set_grad2", &GossipContext::set_grad2)
         .def("set_timeout", &GossipContext::set_timeout)
         .def("set_segments", &GossipContext::set_segments)
+        .def("set_pipe", &GossipContext::set_pipe)
+        .def("pipe", &GossipContext::pipe)
         .def("segments", &GossipContext::segments)
         .def("max_grid", &GossipContext::max_grid)
         .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))

@@ -4,6 +4,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -35,8 +37,11 @@ cudaError_t bn_launch_bwd_dx(int dtype, int mode, const void* dz, const void* x,
                              long long M, int C, cudaStream_t st);
 }
 
+extern std::atomic<long long> g_sgp_kernel_launches;       // bindings.cpp
+
 #define BN_CHECK(expr)                                                                   \
     do {                                                                                 \
+        if (std::strstr(#expr, "_launch_") != nullptr) ++g_sgp_kernel_launches;          \
         cudaError_t _e = (expr);                                                         \
         if (_e != cudaSuccess)                                                           \
             throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
@@ -210,14 +215,20 @@ cudaError_t stem_launch_fwd(const void* x, const void* w, void* y, int N, int H,
                             cudaStream_t st);
 cudaError_t stem_launch_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W,
                               int OH, int OW, cudaStream_t st);
+cudaError_t stem_launch_fwd_f32(const void* x, const void* w, void* y, int N, int H, int W, int OH, int OW,
+                                cudaStream_t st);
+cudaError_t stem_launch_wgrad_f32(const void* x, const void* dy, float* dw_acc, int N, int H, int W,
+                                  int OH, int OW, cudaStream_t st);
 }
 
 static bool stem_can_fuse(const torch::Tensor& x, const torch::Tensor& w)
 {
-    return x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == torch::kBFloat16
+    // bf16 (mma.sync bf16) or fp32 operands (mma.sync TF32), same dtype for both
+    return x.is_cuda() && x.dim() == 4 && x.size(1) == 3
+        && (x.scalar_type() == torch::kBFloat16 || x.scalar_type() == torch::kFloat32)
         && x.is_contiguous(at::MemoryFormat::ChannelsLast)
         && w.dim() == 4 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 7 && w.size(3) == 7
-        && w.scalar_type() == torch::kBFloat16 && w.is_contiguous(at::MemoryFormat::ChannelsLast)
+        && w.scalar_type() == x.scalar_type() && w.is_contiguous(at::MemoryFormat::ChannelsLast)
         && x.size(2) >= 7 && x.size(3) >= 7;
 }
 
@@ -228,23 +239,32 @@ static torch::Tensor stem_forward(torch::Tensor x, torch::Tensor w)
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
     c10::cuda::CUDAGuard guard(x.get_device());
     auto y = torch::empty({N, 64, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-    BN_CHECK(stem_launch_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, OH, OW,
-                             at::cuda::getCurrentCUDAStream()));
+    if (x.scalar_type() == torch::kFloat32)
+        BN_CHECK(stem_launch_fwd_f32(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, OH, OW,
+                                     at::cuda::getCurrentCUDAStream()));
+    else
+        BN_CHECK(stem_launch_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, OH, OW,
+                                 at::cuda::getCurrentCUDAStream()));
     return y;
 }
 
 // returns dW as an fp32 [64, 3, 7, 7] tensor in channels_last layout
 static torch::Tensor stem_wgrad(torch::Tensor x, torch::Tensor dy)
 {
-    TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && x.is_contiguous(at::MemoryFormat::ChannelsLast));
-    TORCH_CHECK(dy.scalar_type() == torch::kBFloat16 && dy.size(1) == 64);
+    TORCH_CHECK((x.scalar_type() == torch::kBFloat16 || x.scalar_type() == torch::kFloat32) &&
+                x.is_contiguous(at::MemoryFormat::ChannelsLast));
+    TORCH_CHECK(dy.scalar_type() == x.scalar_type() && dy.size(1) == 64);
     if (!dy.is_contiguous(at::MemoryFormat::ChannelsLast)) dy = dy.contiguous(at::MemoryFormat::ChannelsLast);
     const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
     const int OH = (int)dy.size(2), OW = (int)dy.size(3);
     c10::cuda::CUDAGuard guard(x.get_device());
     auto acc = torch::zeros({64, 7, 7, 3}, x.options().dtype(torch::kFloat32));
-    BN_CHECK(stem_launch_wgrad(x.data_ptr(), dy.data_ptr(), acc.data_ptr<float>(), N, H, W, OH, OW,
-                               at::cuda::getCurrentCUDAStream()));
+    if (x.scalar_type() == torch::kFloat32)
+        BN_CHECK(stem_launch_wgrad_f32(x.data_ptr(), dy.data_ptr(), acc.data_ptr<float>(), N, H, W, OH, OW,
+                                       at::cuda::getCurrentCUDAStream()));
+    else
+        BN_CHECK(stem_launch_wgrad(x.data_ptr(), dy.data_ptr(), acc.data_ptr<float>(), N, H, W, OH, OW,
+                                   at::cuda::getCurrentCUDAStream()));
     return acc.permute({0, 3, 1, 2});
 }
 
@@ -253,20 +273,22 @@ static torch::Tensor stem_wgrad(torch::Tensor x, torch::Tensor dy)
 // (conv1x1_kernels.cu)
 // ---------------------------------------------------------------------------
 extern "C" {
-int c1_supported(long long M, int N, int K);
-int c1_partial_rows(long long M, int N, int num_sms);
-void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int* out);
+int c1_supported(long long M, int N, int K, int f32);
+int c1_partial_rows(long long M, int N, int K, int num_sms, int f32);
+void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int f32, int* out);
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
-                           const void* residual, int num_sms, cudaStream_t st);
+                           const void* residual, int num_sms, int f32, cudaStream_t st);
 cudaError_t c1_launch_stats_finalize(const float* partial, int R, int C, const float* gamma, const float* beta,
                                      float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                                      float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
 }
 
-// x: NHWC bf16 activation (4-D channels_last) or [M, K] matrix; w: [N, K, 1, 1] or [N, K], rows contiguous
+// x: NHWC bf16 / fp32 activation (4-D channels_last) or [M, K] matrix; w: [N, K, 1, 1] or [N, K], rows
+// contiguous, same dtype as x (fp32 operands are multiplied as TF32, fp32 accumulate)
 static bool conv1x1_can_fuse(const torch::Tensor& x, const torch::Tensor& w)
 {
-    if (!x.is_cuda() || !w.is_cuda() || x.scalar_type() != torch::kBFloat16 || w.scalar_type() != torch::kBFloat16)
+    if (!x.is_cuda() || !w.is_cuda() || x.scalar_type() != w.scalar_type() ||
+        (x.scalar_type() != torch::kBFloat16 && x.scalar_type() != torch::kFloat32))
         return false;
     if (x.dim() == 4) { if (!x.is_contiguous(at::MemoryFormat::ChannelsLast)) return false; }
     else if (!(x.dim() == 2 && x.is_contiguous())) return false;
@@ -275,7 +297,7 @@ static bool conv1x1_can_fuse(const torch::Tensor& x, const torch::Tensor& w)
     const int K = (int)x.size(1), N = (int)w.size(0);
     if (w.size(1) != K || w.stride(1) != 1 || w.stride(0) != K) return false;
     if ((reinterpret_cast<uintptr_t>(x.data_ptr()) | reinterpret_cast<uintptr_t>(w.data_ptr())) & 15) return false;
-    return c1_supported(x.numel() / K, N, K) != 0;
+    return c1_supported(x.numel() / K, N, K, x.scalar_type() == torch::kFloat32) != 0;
 }
 
 static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
@@ -287,15 +309,15 @@ static torch::Tensor conv1x1_alloc_out(const torch::Tensor& x, int N)
 }
 
 // host-side launch plan of the GEMM for a shape (no GPU needed)
-static py::dict conv1x1_plan(long long M, int N, int K, int num_sms, bool residual)
+static py::dict conv1x1_plan(long long M, int N, int K, int num_sms, bool residual, bool f32)
 {
-    TORCH_CHECK(c1_supported(M, N, K), "unsupported GEMM shape");
+    TORCH_CHECK(c1_supported(M, N, K, f32), "unsupported GEMM shape");
     int v[7];
-    c1_describe_plan(M, N, K, num_sms, residual ? 1 : 0, v);
+    c1_describe_plan(M, N, K, num_sms, residual ? 1 : 0, f32 ? 1 : 0, v);
     py::dict d;
     d["block_n"] = v[0]; d["grid"] = v[1]; d["ctas_per_n"] = v[2]; d["stages"] = v[3];
     d["resident_w"] = v[4] != 0; d["store_slabs"] = v[5]; d["smem_bytes"] = v[6];
-    d["partial_rows"] = c1_partial_rows(M, N, num_sms);
+    d["partial_rows"] = c1_partial_rows(M, N, K, num_sms, f32 ? 1 : 0);
     return d;
 }
 
@@ -313,18 +335,19 @@ static torch::Tensor conv1x1_forward(torch::Tensor x, torch::Tensor w, bool with
     auto y = conv1x1_alloc_out(x, N);
     const bool has_res = residual.has_value() && residual->defined();
     TORCH_CHECK(!(has_res && with_stats));
+    const int f32 = x.scalar_type() == torch::kFloat32 ? 1 : 0;
     if (has_res)
-        TORCH_CHECK(residual->is_cuda() && residual->scalar_type() == torch::kBFloat16 &&
+        TORCH_CHECK(residual->is_cuda() && residual->scalar_type() == x.scalar_type() &&
                     residual->sizes() == y.sizes() && residual->strides() == y.strides() &&
                     (reinterpret_cast<uintptr_t>(residual->data_ptr()) & 15) == 0,
                     "conv1x1_forward: residual must match the output's shape and layout");
     torch::Tensor partial;
     if (with_stats)
-        partial = torch::empty({c1_partial_rows(M, N, sm_count()), 3, N},
+        partial = torch::empty({c1_partial_rows(M, N, K, sm_count(), f32), 3, N},
                                torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
     BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K,
                             with_stats ? partial.data_ptr<float>() : nullptr,
-                            has_res ? residual->data_ptr() : nullptr, sm_count(),
+                            has_res ? residual->data_ptr() : nullptr, sm_count(), f32,
                             at::cuda::getCurrentCUDAStream()));
     return y;
 }
@@ -351,10 +374,11 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
     if (has_res) TORCH_CHECK(residual->sizes() == yraw.sizes() && residual->scalar_type() == yraw.scalar_type()
                              && residual->strides() == yraw.strides());
     const int sms = sm_count();
-    const int R = c1_partial_rows(M, N, sms);
+    const int f32 = x.scalar_type() == torch::kFloat32 ? 1 : 0;
+    const int R = c1_partial_rows(M, N, K, sms, f32);
     auto partial = torch::empty({R, 3, N}, fopt);
     BN_CHECK(c1_launch_gemm(x.data_ptr(), w.data_ptr(), yraw.data_ptr(), M, N, K, partial.data_ptr<float>(),
-                            nullptr, sms, st));
+                            nullptr, sms, f32, st));
     auto coef = torch::empty({4, N}, fopt);      // mean, invstd, scale, shift
     float* mean = coef.data_ptr<float>();
     float* rm = nullptr; float* rv = nullptr; long long* nbt = nullptr;
@@ -368,17 +392,69 @@ static std::vector<torch::Tensor> conv1x1_bn_forward(torch::Tensor x, torch::Ten
                                       beta.data_ptr<float>(), rm, rv, nbt, (float)momentum, (float)eps,
                                       mean, mean + N, mean + 2 * N, mean + 3 * N, st));
     auto out = torch::empty_like(yraw);
-    BN_CHECK(bn_launch_apply(0, relu ? 1 : 0, has_res ? 1 : 0, yraw.data_ptr(),
+    BN_CHECK(bn_launch_apply(f32, relu ? 1 : 0, has_res ? 1 : 0, yraw.data_ptr(),
                              has_res ? residual->data_ptr() : nullptr, mean + 2 * N, mean + 3 * N,
                              out.data_ptr(), M, N, st));
     return {yraw, out, coef};
 }
 
+// ---------------------------------------------------------------------------
+// fused softmax cross-entropy + top-1 / top-5 accuracy (csrc/loss_kernels.cu)
+// ---------------------------------------------------------------------------
+extern "C" {
+cudaError_t xent_launch_fwd(int dtype, const void* logits, const long long* target, float* lse, float* out3, int B,
+                            int C, cudaStream_t st);
+cudaError_t xent_launch_bwd(int dtype, const void* logits, const long long* target, const float* lse,
+                            const float* grad_out, void* dlogits, int B, int C, cudaStream_t st);
+}
+
+static bool xent_can_fuse(const torch::Tensor& logits, const torch::Tensor& target)
+{
+    return logits.is_cuda() && target.is_cuda() && logits.dim() == 2 && logits.is_contiguous() &&
+           (logits.scalar_type() == torch::kFloat32 || logits.scalar_type() == torch::kBFloat16) &&
+           target.dim() == 1 && target.scalar_type() == torch::kInt64 && target.is_contiguous() &&
+           target.size(0) == logits.size(0) && logits.size(0) > 0 && logits.size(1) > 0;
+}
+
+// returns (metrics[3] = mean loss, prec@1 %, prec@5 %; lse[B])
+static std::vector<torch::Tensor> xent_forward(torch::Tensor logits, torch::Tensor target)
+{
+    TORCH_CHECK(xent_can_fuse(logits, target), "xent_forward: unsupported tensors");
+    c10::cuda::CUDAGuard guard(logits.get_device());
+    auto st = at::cuda::getCurrentCUDAStream();
+    auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(logits.device());
+    const int B = (int)logits.size(0), C = (int)logits.size(1);
+    auto out3 = torch::empty({3}, fopt);
+    auto lse = torch::empty({B}, fopt);
+    BN_CHECK(cudaMemsetAsync(out3.data_ptr(), 0, 3 * sizeof(float), st));
+    BN_CHECK(xent_launch_fwd(dtype_code(logits), logits.data_ptr(),
+                             reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
+                             lse.data_ptr<float>(), out3.data_ptr<float>(), B, C, st));
+    return {out3, lse};
+}
+
+static torch::Tensor xent_backward(torch::Tensor logits, torch::Tensor target, torch::Tensor lse,
+                                   torch::Tensor grad_out)
+{
+    TORCH_CHECK(xent_can_fuse(logits, target) && lse.is_cuda() && lse.scalar_type() == torch::kFloat32 &&
+                grad_out.is_cuda() && grad_out.scalar_type() == torch::kFloat32 && grad_out.numel() == 1);
+    c10::cuda::CUDAGuard guard(logits.get_device());
+    auto dl = torch::empty_like(logits);
+    BN_CHECK(xent_launch_bwd(dtype_code(logits), logits.data_ptr(),
+                             reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), lse.data_ptr<float>(),
+                             grad_out.data_ptr<float>(), dl.data_ptr(), (int)logits.size(0), (int)logits.size(1),
+                             at::cuda::getCurrentCUDAStream()));
+    return dl;
+}
+
 void bind_bn(py::module& mod)
 {
+    mod.def("xent_can_fuse", &xent_can_fuse);
+    mod.def("xent_forward", &xent_forward);
+    mod.def("xent_backward", &xent_backward);
     mod.def("conv1x1_can_fuse", &conv1x1_can_fuse);
     mod.def("conv1x1_plan", &conv1x1_plan, py::arg("M"), py::arg("N"), py::arg("K"), py::arg("num_sms") = 148,
-            py::arg("residual") = false);
+            py::arg("residual") = false, py::arg("f32") = false);
     mod.def("conv1x1_forward", &conv1x1_forward, py::arg("x"), py::arg("w"), py::arg("with_stats") = false,
             py::arg("residual") = py::none());
     mod.def("conv1x1_bn_forward", &conv1x1_bn_forward);

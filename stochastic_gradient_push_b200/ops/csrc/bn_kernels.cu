@@ -24,6 +24,15 @@
 #define BN_THREADS 256
 #define BN_VEC 8
 #define BN_UNROLL 4
+// rows in flight per thread and tensor.  A thread's vector is 8 channels = 16 B of bf16 but 32 B
+// of fp32 (8 registers per load), so fp32 uses half the unroll: the same bytes in flight and the
+// same register footprint as bf16.  (With the bf16 unroll the fp32 instantiations spilled 250-460
+// bytes per thread under their 64 / 80-register caps and ran at 58-71 % of the HBM roofline
+// instead of 78-94 %: profiles/launches_r2_fp32_bs256_before_tf32_gemm_summary.json.)
+template <typename T> struct Unroll {
+    static constexpr int N = sizeof(T) == 4 ? 2 : 4;        // stats / apply / dx
+    static constexpr int RED = sizeof(T) == 4 ? 1 : 2;      // backward reduce (up to 3 tensors)
+};
 
 namespace {
 
@@ -93,12 +102,13 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, long long 
 #pragma unroll
             for (int i = 0; i < 8; ++i) krow[i] = k.v[i];
         }
-        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
-            typename Io<T>::raw_t raw[BN_UNROLL];
+        constexpr int UN = Unroll<T>::N;
+        for (; r + (UN - 1) * stride < M; r += UN * stride) {
+            typename Io<T>::raw_t raw[UN];
 #pragma unroll
-            for (int u = 0; u < BN_UNROLL; ++u) raw[u] = Io<T>::load_raw(base + (r + u * stride) * C);
+            for (int u = 0; u < UN; ++u) raw[u] = Io<T>::load_raw(base + (r + u * stride) * C);
 #pragma unroll
-            for (int u = 0; u < BN_UNROLL; ++u) {
+            for (int u = 0; u < UN; ++u) {
                 const F8 d = Io<T>::decode(raw[u]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -216,7 +226,7 @@ __global__ void bn_eval_coeff_kernel(int C, const float* __restrict__ gamma, con
 // forward: apply   y = act(x*scale + shift [+ res])
 // ---------------------------------------------------------------------------
 template <typename T, bool RELU, bool ADD>
-__global__ void __launch_bounds__(BN_THREADS, 4)
+__global__ void __launch_bounds__(BN_THREADS, (sizeof(T) == 4 && ADD) ? 3 : 4)     // fp32 + residual: 80 registers
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ scale,
                 const float* __restrict__ shift, T* __restrict__ y, long long M, int C)
 {
@@ -226,10 +236,11 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
     const F8 sh = load_c8(shift + mp.cv * BN_VEC);
     const long long stride = (long long)gridDim.x * mp.rpi;
     const long long off = mp.cv * BN_VEC;
-    for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += BN_UNROLL * stride) {
-        typename Io<T>::raw_t dr[BN_UNROLL], ar[BN_UNROLL];
+    constexpr int UN = Unroll<T>::N;
+    for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += UN * stride) {
+        typename Io<T>::raw_t dr[UN], ar[UN];
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
             const long long rr = r + u * stride;
             if (rr < M) {
                 dr[u] = Io<T>::load_raw(x + rr * C + off);
@@ -237,7 +248,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
             }
         }
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
             const long long rr = r + u * stride;
             if (rr < M) {
                 const F8 d = Io<T>::decode(dr[u]);
@@ -280,10 +291,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
         F8 sc, sh;
         if (MODE == 1) { sc = load_c8(scale + off); sh = load_c8(shift + off); }
         const long long stride = (long long)gridDim.x * mp.rpi;
-        for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += 2 * stride) {
-            typename Io<T>::raw_t gr[2], xr[2], yr[2];
+        constexpr int UN = Unroll<T>::RED;
+        for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += UN * stride) {
+            typename Io<T>::raw_t gr[UN], xr[UN], yr[UN];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < UN; ++u) {
                 const long long rr = r + u * stride;
                 if (rr < M) {
                     gr[u] = Io<T>::load_raw(dy + rr * C + off);
@@ -292,7 +304,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < UN; ++u) {
                 const long long rr = r + u * stride;
                 if (rr < M) {
                     const F8 g = Io<T>::decode(gr[u]);
@@ -356,10 +368,11 @@ bn_bwd_dx_kernel(const T* __restrict__ dz_in, const T* __restrict__ x, const flo
     F8 sh;
     if (MODE == 1) sh = load_c8(shift + off);
     const long long stride = (long long)gridDim.x * mp.rpi;
-    for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += BN_UNROLL * stride) {
-        typename Io<T>::raw_t gr[BN_UNROLL], xr[BN_UNROLL];
+    constexpr int UN = Unroll<T>::N;
+    for (long long r = (long long)blockIdx.x * mp.rpi + mp.rl; r < M; r += UN * stride) {
+        typename Io<T>::raw_t gr[UN], xr[UN];
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
             const long long rr = r + u * stride;
             if (rr < M) {
                 gr[u] = Io<T>::load_raw(dz_in + rr * C + off);
@@ -367,7 +380,7 @@ bn_bwd_dx_kernel(const T* __restrict__ dz_in, const T* __restrict__ x, const flo
             }
         }
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
             const long long rr = r + u * stride;
             if (rr < M) {
                 const F8 g = Io<T>::decode(gr[u]);
@@ -442,7 +455,7 @@ cudaError_t bn_launch_apply(int dtype, int relu, int add, const void* x, const v
                             const float* scale, const float* shift, void* y, long long M, int C,
                             cudaStream_t st)
 {
-    const int G = bn_grid(M, C, 8);
+    const int G = bn_grid(M, C, (dtype == 1 && add) ? 6 : 8);   // fp32 + residual holds 3 CTAs/SM: 2 waves
     if (dtype == 0) {
         if (relu && add) BN_APPLY(__nv_bfloat16, true, true);
         else if (relu)   BN_APPLY(__nv_bfloat16, true, false);

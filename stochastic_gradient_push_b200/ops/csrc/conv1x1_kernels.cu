@@ -50,14 +50,23 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;                 // rows per tile == TMEM lanes == UMMA_M
-constexpr int BK = 64;                  // bf16 per k-block == one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;    // 16 KB
-constexpr int SLAB_BYTES = 32 * 128;    // one epilogue warp's store slab: 32 rows x 64 bf16, 4 KB
+constexpr int ROW_BYTES = 128;          // one k-block row == one 128-byte swizzle row: 64 bf16 or 32 fp32
+constexpr int A_BYTES = BM * ROW_BYTES; // 16 KB
+constexpr int SLAB_BYTES = 32 * 128;    // one epilogue warp's store slab: 32 rows x 128 B (64 bf16 / 32 fp32), 4 KB
+// Element-type dependent tile geometry.  F32 = fp32 activations / weights multiplied on the tensor
+// cores as TF32 (tcgen05.mma.kind::tf32 reads fp32 words from shared memory and uses their top 19
+// bits: the same arithmetic as the reference's cuDNN TF32 convolutions), fp32 accumulate, fp32 out.
+template <bool F32> struct Elt {
+    static constexpr int BYTES = F32 ? 4 : 2;
+    static constexpr int BK = ROW_BYTES / BYTES;      // elements per k-block: 32 / 64
+    static constexpr int UMMA_K = 32 / BYTES;         // 8 (tf32) / 16 (bf16): 32 bytes of K per instruction
+    static constexpr int COLS = ROW_BYTES / BYTES;    // output columns per store slab: 32 / 64
+};
 constexpr int kThreads = 320;           // producer warp, MMA warp, 2 x 4 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
@@ -158,6 +167,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once every MMA issued so far has retired (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
@@ -209,7 +228,7 @@ struct C1Plan {            // host-computed shared-memory plan (bytes are multip
 };
 
 // MODE 0: Y = X.W^T          MODE 1: + BatchNorm statistics of Y          MODE 2: Y = X.W^T + R
-template <int BN, int MODE>
+template <int BN, int MODE, bool F32>
 __global__ void __launch_bounds__(kThreads, 1)
 c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r, int M, int N,
@@ -217,8 +236,11 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 {
     constexpr bool STATS = MODE == 1;
     constexpr bool RES = MODE == 2;
-    constexpr int B_BYTES = BN * BK * 2;
-    constexpr int NS = BN / 64;               // 64-column sub-tiles per tile
+    constexpr int BK = Elt<F32>::BK;
+    constexpr int UMMA_K = Elt<F32>::UMMA_K;
+    constexpr int COLS = Elt<F32>::COLS;
+    constexpr int B_BYTES = BN * ROW_BYTES;
+    constexpr int NS = BN / COLS;             // store-slab wide sub-tiles per tile (64 bf16 / 32 fp32 columns)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -295,7 +317,9 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         if (lane == 0) {
             // cute::UMMA::InstrDescriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
             // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+            // (tf32: A/B format code 2)
+            constexpr uint32_t fmt = F32 ? 2u : 1u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                        ((uint32_t)(BM >> 4) << 24);
             if (resident) { mbar_wait(wfull, 0); tc_fence_after(); }
             int stage = 0;
@@ -314,9 +338,14 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ptr));
                     const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ptr));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per UMMA_K inside the swizzle row
-                        umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                  (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < BK / UMMA_K; ++k) {    // +32 B per UMMA_K inside the swizzle row
+                        if (F32)
+                            umma_tf32(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                      (uint32_t)((kb | k) != 0));
+                        else
+                            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                      (uint32_t)((kb | k) != 0));
+                    }
                     umma_commit(&empty[stage]);                 // smem slot free once these MMAs retire
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -377,8 +406,8 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     __syncwarp();
                 }
                 uint32_t v[64];
-                tmem_ld32(t_row + (uint32_t)(s * 64), v);
-                tmem_ld32(t_row + (uint32_t)(s * 64 + 32), v + 32);
+                tmem_ld32(t_row + (uint32_t)(s * COLS), v);
+                if (!F32) tmem_ld32(t_row + (uint32_t)(s * COLS + 32), v + 32);
                 tmem_ld_wait();
                 if (s == NS - 1) {                                 // accumulator fully read: hand it back
                     tc_fence_before();
@@ -410,22 +439,32 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                             const uint32_t rr[4] = {r0, r1, r2, r3};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                v[8 * i + 2 * e] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e]) +
-                                                                   __uint_as_float(rr[e] << 16));
-                                v[8 * i + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e + 1]) +
-                                                                       __uint_as_float(rr[e] & 0xFFFF0000u));
+                                if (F32) {
+                                    v[4 * i + e] = __float_as_uint(__uint_as_float(v[4 * i + e]) +
+                                                                   __uint_as_float(rr[e]));
+                                } else {
+                                    v[8 * i + 2 * e] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e]) +
+                                                                       __uint_as_float(rr[e] << 16));
+                                    v[8 * i + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * i + 2 * e + 1]) +
+                                                                           __uint_as_float(rr[e] & 0xFFFF0000u));
+                                }
                             }
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                                     "r"(pack_bf16(v[8 * i + 0], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
-                                     "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
-                                     : "memory");
+                        if (F32)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * i + 0]),
+                                         "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
+                                         : "memory");
+                        else
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                                         "r"(pack_bf16(v[8 * i + 0], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
+                                         "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
+                                         : "memory");
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> TMA reads
                 __syncwarp();
                 if (lane == 0) {
-                    if (nrows > 0) tma_store_2d(&tm_y, slab, nb * BN + s * 64, mt * BM + q * 32);
+                    if (nrows > 0) tma_store_2d(&tm_y, slab, nb * BN + s * COLS, mt * BM + q * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     if (RES) {                                     // fetch the next residual slab
                         const int nmt = (s + 1 < NS) ? mt : mt + tile_step;
@@ -436,7 +475,7 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nbar),
                                          "r"(SLAB_BYTES)
                                          : "memory");
-                            tma_load_2d_s(&tm_r, nbar, slab0 + (uint32_t)((slot ^ 1) * SLAB_BYTES), nb * BN + ns * 64,
+                            tma_load_2d_s(&tm_r, nbar, slab0 + (uint32_t)((slot ^ 1) * SLAB_BYTES), nb * BN + ns * COLS,
                                           nmt * BM + q * 32, L2_EVICT_FIRST);
                         }
                     }
@@ -446,7 +485,7 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     if (!have_k) {
                         uint32_t u;
                         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(rd + (uint32_t)(rd_chunk << 4)));
-                        k0[s] = __uint_as_float(u << 16);
+                        k0[s] = F32 ? __uint_as_float(u) : __uint_as_float(u << 16);
                         k1[s] = __uint_as_float(u & 0xFFFF0000u);
                     }
                     if (nrows == 32) {
@@ -459,10 +498,12 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                                              : "r"(rd + (uint32_t)((r8 + i) * 128 + ((rd_chunk ^ i) << 4))));
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float d0 = __uint_as_float(u[i] << 16) - k0[s];
-                                const float d1 = __uint_as_float(u[i] & 0xFFFF0000u) - k1[s];
+                                const float d0 = (F32 ? __uint_as_float(u[i]) : __uint_as_float(u[i] << 16)) - k0[s];
                                 s0[s] += d0; q0[s] = fmaf(d0, d0, q0[s]);
-                                s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                                if (!F32) {          // fp32: one channel per lane; bf16: a channel pair
+                                    const float d1 = __uint_as_float(u[i] & 0xFFFF0000u) - k1[s];
+                                    s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                                }
                             }
                         }
                     } else {
@@ -470,10 +511,12 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                             uint32_t u;
                             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u)
                                          : "r"(rd + (uint32_t)(r * 128 + ((rd_chunk ^ (r & 7)) << 4))));
-                            const float d0 = __uint_as_float(u << 16) - k0[s];
-                            const float d1 = __uint_as_float(u & 0xFFFF0000u) - k1[s];
+                            const float d0 = (F32 ? __uint_as_float(u) : __uint_as_float(u << 16)) - k0[s];
                             s0[s] += d0; q0[s] = fmaf(d0, d0, q0[s]);
-                            s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                            if (!F32) {
+                                const float d1 = __uint_as_float(u & 0xFFFF0000u) - k1[s];
+                                s1[s] += d1; q1[s] = fmaf(d1, d1, q1[s]);
+                            }
                         }
                     }
                 }
@@ -492,8 +535,12 @@ c1_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             const int e = set * 4 + q;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                sc[e * BN + s * 64 + 2 * lane] = make_float4(cnt, k0[s], s0[s], q0[s]);
-                sc[e * BN + s * 64 + 2 * lane + 1] = make_float4(cnt, k1[s], s1[s], q1[s]);
+                if (F32) {
+                    sc[e * BN + s * COLS + lane] = make_float4(cnt, k0[s], s0[s], q0[s]);
+                } else {
+                    sc[e * BN + s * COLS + 2 * lane] = make_float4(cnt, k0[s], s0[s], q0[s]);
+                    sc[e * BN + s * COLS + 2 * lane + 1] = make_float4(cnt, k1[s], s1[s], q1[s]);
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int t = (int)threadIdx.x - 64;
@@ -644,18 +691,20 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
-// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128B swizzle.  wide_promotion:
+// row-major [rows, cols] bf16 / fp32 matrix, box = [box_rows, 128 bytes of columns], 128B swizzle.  wide_promotion:
 // let L2 fetch 256 B per request -- right for operand tiles whose rows are consumed whole, wrong
 // for the 128 B-per-row output / residual slabs (ncu: +21 % DRAM reads on the residual stream).
-bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int box_rows, bool wide_promotion)
+bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int box_rows, bool wide_promotion,
+              bool f32)
 {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * (f32 ? 4 : 2)};
+    const cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};     // 128 bytes wide
     const cuuint32_t estr[2] = {1u, 1u};
-    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    return fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+              const_cast<void*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
               wide_promotion ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -663,12 +712,48 @@ bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int b
 
 // Tile width: the widest BLOCK_N dividing N unless a narrower one shortens the critical path
 // (waves of row tiles per CTA x BLOCK_N) by more than 10 % -- that only happens when M is small.
-int pick_bn(long long M, int N, int num_sms)
+bool c1_f32_prefer_resident()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SGP_B200_C1_F32_RESIDENT");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
+int bn_override()        // SGP_B200_C1_BN=64|128|256 forces a tile width (benchmarking)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SGP_B200_C1_BN");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+// can the CTA's whole W block stay resident next to a >= 3-deep X ring and one slab per epilogue warp?
+bool fits_resident(int bn, int K, bool f32)
+{
+    const int bk = f32 ? Elt<true>::BK : Elt<false>::BK;
+    const int k_blocks = (K + bk - 1) / bk;
+    return SMEM_LIMIT - SMEM_FIXED - 8 * SLAB_BYTES - k_blocks * bn * ROW_BYTES >= 3 * A_BYTES;
+}
+
+int pick_bn(long long M, int N, int K, int num_sms, bool f32)
 {
     const long long m_tiles = (M + BM - 1) / BM;
     int best = 0;
     long long best_cost = 0;
-    for (int bn = 256; bn >= 64; bn >>= 1) {
+    const int force = bn_override();
+    if (force >= 64 && force <= 256 && N % force == 0) return force;
+    // fp32 operands are twice as wide: prefer the widest tile whose W block stays resident (a
+    // non-resident 256-wide tile re-streams 3x the bytes of X per row tile through L2)
+    int bn_max = 256;
+    if (f32 && c1_f32_prefer_resident())
+        for (int bn = 256; bn >= 128; bn >>= 1)      // (a 64-wide tile re-reads X once per 64 channels)
+            if (N % bn == 0 && fits_resident(bn, K, true)) { bn_max = bn; break; }
+    for (int bn = bn_max; bn >= 64; bn >>= 1) {
         if (N % bn) continue;
         long long per = num_sms / (N / bn);
         if (per < 1) per = 1;
@@ -678,9 +763,9 @@ int pick_bn(long long M, int N, int num_sms)
     return best;
 }
 
-void grid_shape(long long M, int N, int num_sms, int& bn, int& ctas_per_n, int& grid)
+void grid_shape(long long M, int N, int K, int num_sms, bool f32, int& bn, int& ctas_per_n, int& grid)
 {
-    bn = pick_bn(M, N, num_sms);
+    bn = pick_bn(M, N, K, num_sms, f32);
     const int n_blocks = N / bn;
     const long long m_tiles = (M + BM - 1) / BM;
     long long per = num_sms / n_blocks;
@@ -693,10 +778,11 @@ void grid_shape(long long M, int N, int num_sms, int& bn, int& ctas_per_n, int& 
 // Shared-memory plan.  W stays resident when the CTA's [BN, K] block plus a >= 3-deep X ring
 // fits (then every row tile costs one 16 KB X load instead of X + W); the store slabs shrink
 // from 2 to 1 per warp if that is what makes it fit.
-C1Plan make_plan(int bn, int K, int n_blocks, bool residual, int& smem_bytes)
+C1Plan make_plan(int bn, int K, int n_blocks, bool residual, bool f32, int& smem_bytes)
 {
-    const int k_blocks = (K + BK - 1) / BK;
-    const int b_bytes = bn * BK * 2;
+    const int bk = f32 ? Elt<true>::BK : Elt<false>::BK;
+    const int k_blocks = (K + bk - 1) / bk;
+    const int b_bytes = bn * ROW_BYTES;
     C1Plan p;
     p.x_hint_first = n_blocks == 1;
     p.resident = 0;
@@ -714,12 +800,13 @@ C1Plan make_plan(int bn, int K, int n_blocks, bool residual, int& smem_bytes)
     return p;
 }
 
-template <int BN>
+template <int BN, bool F32>
 cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
                    int M, int N, int K, float* partial, int mode, int grid, cudaStream_t st)
 {
-    auto kern = mode == 1 ? c1_gemm_kernel<BN, 1> : (mode == 2 ? c1_gemm_kernel<BN, 2> : c1_gemm_kernel<BN, 0>);
-    static bool configured[3][64] = {};            // function attributes are per device
+    auto kern = mode == 1 ? c1_gemm_kernel<BN, 1, F32>
+                          : (mode == 2 ? c1_gemm_kernel<BN, 2, F32> : c1_gemm_kernel<BN, 0, F32>);
+    static bool configured[3][64] = {};            // function attributes are per device (and per instantiation)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[mode][dev]) {
@@ -728,7 +815,7 @@ cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorM
         if (dev >= 0 && dev < 64) configured[mode][dev] = true;
     }
     int smem = 0;
-    const C1Plan plan = make_plan(BN, K, N / BN, mode == 2, smem);
+    const C1Plan plan = make_plan(BN, K, N / BN, mode == 2, F32, smem);
     if (plan.stages < 2) return cudaErrorInvalidValue;
     kern<<<grid, kThreads, smem, st>>>(tx, tw, ty, tr, M, N, K, partial, plan);
     return cudaGetLastError();
@@ -738,48 +825,59 @@ cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorM
 
 extern "C" {
 
-// shapes the kernel covers: bf16, K % 8 == 0 (16-byte row pitch), N % 64 == 0, M < 2^31
-int c1_supported(long long M, int N, int K)
+// shapes the kernel covers: 16-byte row pitch (K % 8 == 0 for bf16, K % 4 == 0 for fp32), N % 64 == 0,
+// M < 2^31
+int c1_supported(long long M, int N, int K, int f32)
 {
-    return M >= 1 && M < (1ll << 31) && N >= 64 && N % 64 == 0 && K >= 8 && K % 8 == 0;
+    const int kq = f32 ? 4 : 8;
+    return M >= 1 && M < (1ll << 31) && N >= 64 && N % 64 == 0 && K >= 8 && K % kq == 0;
 }
 
 // launch plan for a shape (host logic only; exercised by the CPU tests):
 // out = {BLOCK_N, grid, ctas_per_n, stages, resident, nbuf, dynamic smem bytes}
-void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int* out)
+void c1_describe_plan(long long M, int N, int K, int num_sms, int residual, int f32, int* out)
 {
     int bn, per, grid, smem = 0;
-    grid_shape(M, N, num_sms, bn, per, grid);
-    const C1Plan p = make_plan(bn, K, N / bn, residual != 0, smem);
+    grid_shape(M, N, K, num_sms, f32 != 0, bn, per, grid);
+    const C1Plan p = make_plan(bn, K, N / bn, residual != 0, f32 != 0, smem);
     out[0] = bn; out[1] = grid; out[2] = per; out[3] = p.stages; out[4] = p.resident; out[5] = p.nbuf;
     out[6] = smem;
 }
 
 // number of partial-statistics rows c1_launch_gemm writes for this shape
-int c1_partial_rows(long long M, int N, int num_sms)
+int c1_partial_rows(long long M, int N, int K, int num_sms, int f32)
 {
     int bn, per, grid;
-    grid_shape(M, N, num_sms, bn, per, grid);
+    grid_shape(M, N, K, num_sms, f32 != 0, bn, per, grid);
     return per;              // one merged partial row per CTA
 }
 
-// y[M,N] = x[M,K] . w[N,K]^T (bf16) [+ residual[M,N]]; partial (nullable) = [c1_partial_rows][3][N] fp32
-// statistics of y.  partial and residual are mutually exclusive.
+// y[M,N] = x[M,K] . w[N,K]^T [+ residual[M,N]]; all operands bf16 (f32 == 0) or all fp32 with TF32
+// tensor-core math (f32 != 0); partial (nullable) = [c1_partial_rows][3][N] fp32 statistics of y.
+// partial and residual are mutually exclusive.
 cudaError_t c1_launch_gemm(const void* x, const void* w, void* y, long long M, int N, int K, float* partial,
-                           const void* residual, int num_sms, cudaStream_t st)
+                           const void* residual, int num_sms, int f32, cudaStream_t st)
 {
-    if (!c1_supported(M, N, K) || (partial && residual)) return cudaErrorInvalidValue;
+    if (!c1_supported(M, N, K, f32) || (partial && residual)) return cudaErrorInvalidValue;
     const int mode = partial ? 1 : (residual ? 2 : 0);
+    const bool f = f32 != 0;
     int bn, per, grid;
-    grid_shape(M, N, num_sms, bn, per, grid);
+    grid_shape(M, N, K, num_sms, f, bn, per, grid);
     CUtensorMap tx, tw, ty, tr;
-    if (!make_map(&tx, x, M, K, BM, true) || !make_map(&tw, w, N, K, bn, true) ||
-        !make_map(&ty, y, M, N, 32, false) || !make_map(&tr, residual ? residual : y, M, N, 32, false))
+    if (!make_map(&tx, x, M, K, BM, true, f) || !make_map(&tw, w, N, K, bn, true, f) ||
+        !make_map(&ty, y, M, N, 32, false, f) || !make_map(&tr, residual ? residual : y, M, N, 32, false, f))
         return cudaErrorInvalidValue;
+    if (f) {
+        switch (bn) {
+        case 256: return launch<256, true>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+        case 128: return launch<128, true>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+        default: return launch<64, true>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+        }
+    }
     switch (bn) {
-    case 256: return launch<256>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
-    case 128: return launch<128>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
-    default: return launch<64>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+    case 256: return launch<256, false>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+    case 128: return launch<128, false>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
+    default: return launch<64, false>(tx, tw, ty, tr, (int)M, N, K, partial, mode, grid, st);
     }
 }
 

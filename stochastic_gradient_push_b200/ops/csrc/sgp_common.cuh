@@ -235,6 +235,8 @@ __device__ __forceinline__ bool spin_wait_geq(const uint32_t* flag, uint32_t wan
 // launcher entry points (sgp_kernels.cu)
 extern "C" {
 cudaError_t sgp_launch_step(const SgpArgs* args, int grid, cudaStream_t stream);
+cudaError_t sgp_launch_step_pipe(const SgpArgs* args, int grid, cudaStream_t stream);
+int sgp_max_resident_ctas_pipe(int device);
 cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
 cudaError_t sgp_launch_gather_tma(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
 cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_flag,

@@ -518,6 +518,275 @@ sgp_gather_tma_kernel(const SgpArgs a, const int pub_grid)
 }
 
 // ---------------------------------------------------------------------------
+// Fused step kernel, warp-specialised + TMA-fed variant (the SGP / D-PSGD hot path).
+//
+// sgp_step_kernel pulls the peers' outboxes with register-staged 16-byte loads: every
+// consumer thread has 4 x 16 B in flight and the CTA alternates between an HBM-bound phase 1
+// and an NVLink-bound phase 2 (0.257 ms at ResNet-50 size on 2 GPUs = 52 % of the NVLink
+// roofline, profiles/README.md).  Here the two phases run on different warps of the same CTA:
+//
+//   warps 0-7 (consumers)  for seg = 0..K:   phase 1 of segment `seg`   (SGD + publish, HBM)
+//                                            phase 2 of segment `seg-1` (mix + de-bias)
+//                          phase 2 reads the peers' data from SHARED MEMORY, where it has
+//                          been landing while phase 1 of the next segment was streaming HBM
+//   warp 8 lane 0 (producer) per segment: acquire the in-neighbours' publish flags, then keep
+//                          a ring of PIPE_STAGES x 16 KB bulk copies (cp.async.bulk,
+//                          peer global -> shared, mbarrier complete_tx) in flight over NVLink
+//
+// so the NVLink stream starts as soon as the first segment of the peer is published and
+// never waits for a consumer register to free up; the consumers never wait for NVLink
+// latency.  Flags, outbox layout, acks and the last-CTA epilogue are those of
+// sgp_step_kernel (gather / probe / the old kernel interoperate with it); the grid must be
+// the same on all ranks (flags are matched by CTA index).
+//
+// A timed-out flag wait does not leave stale parameters behind: the producer marks the CTA
+// failed, completes its barriers without data, and the consumers de-bias their own published
+// numerator instead (z = x_own / w1, i.e. "every in-message of this round was lost" -- a valid
+// push-sum state); the sticky status word makes the host raise at its next poll.
+// ---------------------------------------------------------------------------
+#define PIPE_STAGES    4
+#define PIPE_CONSUMERS SGP_THREADS                 // 256: the chunk decomposition of sgp_step_kernel
+#define PIPE_THREADS   (PIPE_CONSUMERS + 32)
+#define PIPE_SMEM      (PIPE_STAGES * SGP_TMA_BYTES + 2 * PIPE_STAGES * 8 + 64)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __maxnreg__(112)
+sgp_step_pipe_kernel(const SgpArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                          // [STAGES][CHUNK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + PIPE_STAGES * SGP_TMA_BYTES);
+    uint64_t* empty = full + PIPE_STAGES;
+    uint64_t* wbar = empty + PIPE_STAGES;            // new push-sum weight is known
+    __shared__ float s_wn;
+    __shared__ int   s_ok;                            // WAR fence outcome (consumers)
+    __shared__ volatile int s_fail;                   // producer: an in-neighbour timed out
+
+    SgpState* st = a.st;
+    const uint32_t step   = *((volatile uint32_t*)&st->step);
+    const uint32_t parity = step & 1u;
+    const uint32_t flags  = a.flags;
+    const int      tid    = threadIdx.x;
+    const int      warp   = tid >> 5;
+    const int      b      = blockIdx.x;
+    const long long nchunks = a.n / SGP_CHUNK;
+
+    RowInfo row;
+    load_row(a, step, row);
+
+    const float w0 = *((volatile float*)&st->ps_weight[parity]);
+    const float wmul = (flags & SGP_F_IN_NUMER) ? 1.f : w0;
+    const float w1 = w0;                              // (no residual fold in the synchronous step)
+
+    SgpSignalPad* mypad = a.pads[a.rank];
+    float* my_out = a.outboxes[a.rank] + (size_t)parity * a.n;
+
+    const long long my_chunks = (nchunks > b) ? (nchunks - 1 - b) / gridDim.x + 1 : 0;
+    int K = a.segments < 1 ? 1 : a.segments;
+    if (K > SGP_SEQ_STRIDE - 1) K = SGP_SEQ_STRIDE - 1;
+    const uint32_t seq_base = step * (uint32_t)SGP_SEQ_STRIDE;
+
+    // compacted in-neighbour list (table entries < 0 are holes)
+    int n_in = 0;
+    int in_rank[SGP_MAX_PEERS];
+    float in_w[SGP_MAX_PEERS];
+#pragma unroll
+    for (int k = 0; k < SGP_MAX_PEERS; ++k)
+        if (k < row.n_in && row.in[k] >= 0) { in_rank[n_in] = row.in[k]; in_w[n_in] = row.in_w[k]; ++n_in; }
+
+    if (tid == 0) {
+        for (int i = 0; i < PIPE_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PIPE_CONSUMERS / 32); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_fail = 0;
+        s_ok = 1;
+    }
+    __syncthreads();
+
+    if (warp == PIPE_CONSUMERS / 32) {
+        // ============================ producer ============================
+        if ((tid & 31) == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            float wn = row.self_w * w1;
+            for (int seg = 0; seg < K; ++seg) {
+                for (int k = 0; k < n_in && ok; ++k) {
+                    const SgpSignalPad* pj = a.pads[in_rank[k]];
+                    ok = spin_wait_geq(&pj->pub_seq[b], seq_base + (uint32_t)seg + 1u, st, a.timeout_ns,
+                                       SGP_ERR_TIMEOUT_PUB);
+                    if (ok && seg == 0) wn = fmaf(in_w[k], ld_relaxed_sys_f32(&pj->psw[parity]), wn);
+                }
+                if (!ok) s_fail = 1;
+                if (seg == 0) {
+                    s_wn = ok ? wn : row.self_w * w1;
+                    __threadfence_block();
+                    mbar_arrive(wbar);
+                }
+                const long long it_lo = my_chunks * seg / K, it_hi = my_chunks * (seg + 1) / K;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    for (int k = 0; k < n_in; ++k) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        if (ok) {
+                            const float* src = a.outboxes[in_rank[k]] + (size_t)parity * a.n + c * SGP_CHUNK;
+                            mbar_expect_tx(&full[stage], SGP_TMA_BYTES);
+                            tma_load_1d(ring + (size_t)stage * SGP_CHUNK, src, SGP_TMA_BYTES, &full[stage]);
+                        } else {
+                            mbar_arrive(&full[stage]);           // nothing will land: release the consumers
+                        }
+                        if (++stage == PIPE_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ consumers ============================
+        const SgpHyper hp = *a.hyper;
+        const uint64_t pol_first = l2_evict_first_policy();
+        const uint64_t pol_last = l2_evict_last_policy();
+        const bool do_sgd = (flags & SGP_F_SGD) && (hp.do_sgd != 0.f);
+        const int lane = tid & 31;
+
+        if (step >= st->ack_from + 2u) {
+            // WAR fence: outbox[parity] was last read at step-2 by that step's out-neighbours
+            if (tid == 0) {
+                RowInfo prev;
+                load_row(a, step - 2u, prev);
+                int ok = 1;
+                for (int k = 0; k < prev.n_out; ++k) {
+                    const int o = prev.out[k];
+                    if (o == a.rank || o < 0) continue;
+                    ok &= spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_ACK) ? 1 : 0;
+                }
+                s_ok = ok;
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(PIPE_CONSUMERS) : "memory");
+        }
+
+        int cstage = 0;
+        uint32_t cphase = 0;
+        float inv_wn = 1.f;
+        const float inv_w1 = 1.f / w1;
+
+        for (int seg = 0; seg <= K; ++seg) {
+            // ---------------- phase 1 of segment `seg`: local update + publish ----------------
+            if (seg < K) {
+                const long long it_lo = my_chunks * seg / K, it_hi = my_chunks * (seg + 1) / K;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+                    float4 x[SGP_UNROLL], g[SGP_UNROLL], m[SGP_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        x[u] = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
+                        if (do_sgd) {
+                            if (flags & SGP_F_GRAD_BF16)
+                                g[u] = bf16x4_to_f4(ld_once_u2(reinterpret_cast<const uint2*>(
+                                           reinterpret_cast<const __nv_bfloat16*>(a.g) + i), pol_first));
+                            else
+                                g[u] = ld_once_f4(reinterpret_cast<const float4*>(
+                                           reinterpret_cast<const float*>(a.g) + i), pol_first);
+                            if (a.g2 != nullptr) {
+                                const float4 h = ld_once_f4(reinterpret_cast<const float4*>(a.g2 + i), pol_first);
+                                g[u].x += h.x; g[u].y += h.y; g[u].z += h.z; g[u].w += h.w;
+                            }
+                            m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        float4 xv = mul4(x[u], wmul);
+                        if (do_sgd) {
+                            float4 gv = mul4(g[u], hp.grad_scale);
+                            float4 mv = m[u];
+                            sgd1(xv.x, gv.x, mv.x, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                            sgd1(xv.y, gv.y, mv.y, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                            sgd1(xv.z, gv.z, mv.z, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                            sgd1(xv.w, gv.w, mv.w, hp.lr, hp.momentum, hp.weight_decay, hp.nesterov);
+                            st_f4(reinterpret_cast<float4*>(a.m + i), mv);
+                            if (flags & SGP_F_ZERO_GRAD) {
+                                if (flags & SGP_F_GRAD_BF16)
+                                    st_u2(reinterpret_cast<uint2*>(
+                                              reinterpret_cast<__nv_bfloat16*>(a.g) + i), make_uint2(0u, 0u));
+                                else
+                                    st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.g) + i),
+                                          make_float4(0.f, 0.f, 0.f, 0.f));
+                                if (a.g2 != nullptr)
+                                    st_f4(reinterpret_cast<float4*>(a.g2 + i), make_float4(0.f, 0.f, 0.f, 0.f));
+                            }
+                        }
+                        st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(PIPE_CONSUMERS) : "memory");
+                if (tid == 0) {
+                    if (seg == 0) st_relaxed_sys_f32(&mypad->psw[parity], w1);
+                    __threadfence_system();
+                    st_release_sys(&mypad->pub_seq[b], seq_base + (uint32_t)seg + 1u);
+                }
+            }
+            // ---------------- phase 2 of segment `seg - 1`: mix + de-bias ----------------
+            if (seg >= 1) {
+                const int ps = seg - 1;
+                if (ps == 0) {
+                    mbar_wait(wbar, 0);
+                    inv_wn = 1.f / s_wn;
+                }
+                const long long it_lo = my_chunks * ps / K, it_hi = my_chunks * (ps + 1) / K;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+                    float4 own[SGP_UNROLL], acc[SGP_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        own[u] = ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first);   // L2 hit
+                        acc[u] = mul4(own[u], row.self_w);
+                    }
+                    for (int k = 0; k < n_in; ++k) {
+                        mbar_wait(&full[cstage], cphase);
+                        const float4* src = reinterpret_cast<const float4*>(ring + (size_t)cstage * SGP_CHUNK);
+                        const float wk = in_w[k];
+#pragma unroll
+                        for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(src[tid + u * SGP_THREADS], wk, acc[u]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[cstage]);     // this warp is done with the stage
+                        if (++cstage == PIPE_STAGES) { cstage = 0; cphase ^= 1u; }
+                    }
+                    const bool failed = s_fail != 0;
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        const float4 zv = failed ? mul4(own[u], inv_w1) : mul4(acc[u], inv_wn);
+                        st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                        if (flags & SGP_F_SHADOW)
+                            st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- epilogue: last CTA publishes state + acks ------------
+    __syncthreads();
+    if (tid == 0 && cta_done_is_last(st)) {
+        for (int k = 0; k < n_in; ++k)
+            if (in_rank[k] != a.rank) st_release_sys(&a.pads[in_rank[k]]->ack_seq[a.rank], step + 1u);
+        *((volatile float*)&st->ps_weight[parity ^ 1u]) = s_wn;
+        *((volatile uint32_t*)&st->done_ctas) = 0u;
+        *((volatile uint32_t*)&st->step) = step + 1u;
+        __threadfence();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // AD-PSGD passive poll: did the in-neighbour of the current round publish?
 // ---------------------------------------------------------------------------
 __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* host_flag)
@@ -708,6 +977,32 @@ cudaError_t sgp_launch_step(const SgpArgs* args, int grid, cudaStream_t stream)
 {
     sgp_step_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args);
     return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_step_pipe(const SgpArgs* args, int grid, cudaStream_t stream)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PIPE_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    sgp_step_pipe_kernel<<<grid, PIPE_THREADS, PIPE_SMEM, stream>>>(*args);
+    return cudaGetLastError();
+}
+
+// co-resident CTAs of the pipelined step kernel (dynamic shared memory bound)
+int sgp_max_resident_ctas_pipe(int device)
+{
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgp_step_pipe_kernel, PIPE_THREADS, PIPE_SMEM)
+        != cudaSuccess) return 0;
+    return sms * per_sm;
 }
 
 cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream)

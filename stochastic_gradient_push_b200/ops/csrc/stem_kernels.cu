@@ -294,7 +294,274 @@ stem_wgrad_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ d
     }
 }
 
+// ===========================================================================
+// fp32 activations / weights, TF32 tensor-core math (mma.sync.m16n8k8.tf32): the
+// precision-matched flagship path (the reference's cuDNN runs this layer in TF32 too, with
+// generic kernels: 2.60 ms forward + 2.58 ms wgrad at batch 256 in
+// profiles/launches_r2_fp32_bs256_before_tf32_gemm_summary.json).
+// Same tiling as the bf16 kernels; fp32 words in shared memory, so no pair-packing tricks:
+//   fprop : Y[128 x 64] = A[128 x 152] * W^T[152 x 64]      (K 147 -> 152 = 19 k-steps of 8)
+//   wgrad : dW[64 x 152] += dY^T[64 x 128] * A[128 x 152]   (K = the tile's 128 pixels)
+// ===========================================================================
+#define ST_K32 152                    // K padded to 19 mma k-steps of 8
+#define ST_W32PITCH 156               // == 28 (mod 32): B-fragment loads are bank-conflict free
+
+namespace {
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 "
+        "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void patch_fetch_f32(float (&reg)[ST_PATCH_PER_THREAD], const float* __restrict__ x,
+                                                TileCoord tc, int H, int W)
+{
+    const int ih0 = 2 * tc.oh0 - 3, iw0 = 2 * tc.ow0 - 3;
+#pragma unroll
+    for (int i = 0; i < ST_PATCH_PER_THREAD; ++i) {
+        const int e = threadIdx.x + i * ST_THREADS;
+        const int r = e / ST_PITCH, c = e - r * ST_PITCH;       // c = col*3 + ci
+        const int ih = ih0 + r, iw = iw0 + c / 3;
+        float v = 0.f;
+        if (e < ST_PATCH_ELEMS && c < ST_PC * 3 && ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = __ldg(x + ((size_t)(tc.n * H + ih) * W + iw) * 3 + (c % 3));
+        reg[i] = v;
+    }
+}
+
+__device__ __forceinline__ void patch_commit_f32(float* patch, const float (&reg)[ST_PATCH_PER_THREAD])
+{
+#pragma unroll
+    for (int i = 0; i < ST_PATCH_PER_THREAD; ++i) {
+        const int e = threadIdx.x + i * ST_THREADS;
+        if (e < ST_PATCH_ELEMS) patch[e] = reg[i];
+    }
+}
+
+}  // namespace
+
+// dynamic shared memory: [ s_w : 64 x 156 fp32 ][ s_patch : 21 x 112 (+8) fp32 ][ koff : 152 int16 ]
+#define ST_F32_FWD_SMEM (ST_CO * ST_W32PITCH * 4 + (ST_PATCH_ELEMS + 8) * 4 + ST_K32 * 2 + 16)
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_fwd_tf32_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                     int N, int H, int W, int OH, int OW)
+{
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float* s_w = reinterpret_cast<float*>(st_smem);                             // [co][k], pads ZERO
+    float* s_patch = s_w + ST_CO * ST_W32PITCH;
+    int16_t* s_koff = reinterpret_cast<int16_t*>(s_patch + ST_PATCH_ELEMS + 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    for (int e = tid; e < ST_CO * ST_W32PITCH; e += ST_THREADS) {
+        const int co = e / ST_W32PITCH, k = e - co * ST_W32PITCH;
+        s_w[e] = (k < ST_K) ? w[co * ST_K + k] : 0.f;
+    }
+    for (int k = tid; k < ST_K32; k += ST_THREADS)          // padded taps read a finite word (x 0)
+        s_koff[k] = (k < ST_K) ? (int16_t)((k / 21) * ST_PITCH + (k % 21)) : (int16_t)0;
+    if (tid < 8) s_patch[ST_PATCH_ELEMS + tid] = 0.f;
+
+    const int tiles_w = (OW + ST_TW - 1) / ST_TW, tiles_h = (OH + ST_TH - 1) / ST_TH;
+    const long long n_tiles = (long long)N * tiles_h * tiles_w;
+
+    float pre[ST_PATCH_PER_THREAD];
+    if ((long long)blockIdx.x < n_tiles) patch_fetch_f32(pre, x, tile_coord(blockIdx.x, tiles_h, tiles_w), H, W);
+
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(t, tiles_h, tiles_w);
+        __syncthreads();                      // previous tile's patch fully consumed
+        patch_commit_f32(s_patch, pre);
+        __syncthreads();
+        if (t + gridDim.x < n_tiles)          // next tile's loads fly during this tile's math
+            patch_fetch_f32(pre, x, tile_coord(t + gridDim.x, tiles_h, tiles_w), H, W);
+
+        // warp `warp` owns output row pr = warp: pixels (pr, gid) and (pr, gid + 8)
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+        const float* p0 = s_patch + (2 * warp) * ST_PITCH + 6 * gid;
+        const float* p1 = p0 + 6 * 8;
+#pragma unroll 2
+        for (int ks = 0; ks < ST_K32 / 8; ++ks) {
+            const int k0 = ks * 8 + tig;
+            const int o0 = s_koff[k0], o1 = s_koff[k0 + 4];
+            uint32_t a[4];
+            a[0] = __float_as_uint(p0[o0]);
+            a[1] = __float_as_uint(p1[o0]);
+            a[2] = __float_as_uint(p0[o1]);
+            a[3] = __float_as_uint(p1[o1]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* wr = s_w + (j * 8 + gid) * ST_W32PITCH + k0;
+                uint32_t b[2];
+                b[0] = __float_as_uint(wr[0]);
+                b[1] = __float_as_uint(wr[4]);
+                mma_tf32_1688(acc[j], a, b);
+            }
+        }
+
+        // C fragment: (pixel gid | gid+8, channels j*8 + 2*tig, +1): four adjacent lanes fill one
+        // 32-byte sector, so the fragments are stored directly (no staging tile)
+        const int oh = tc.oh0 + warp;
+        if (oh < OH) {
+            const int ow_a = tc.ow0 + gid, ow_b = ow_a + 8;
+            float* ya = y + (((size_t)tc.n * OH + oh) * OW + ow_a) * ST_CO + 2 * tig;
+            float* yb = ya + (size_t)8 * ST_CO;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (ow_a < OW) *reinterpret_cast<float2*>(ya + j * 8) = make_float2(acc[j][0], acc[j][1]);
+                if (ow_b < OW) *reinterpret_cast<float2*>(yb + j * 8) = make_float2(acc[j][2], acc[j][3]);
+            }
+        }
+    }
+}
+
+// weight gradient, fp32 / TF32: dw_acc[co][k] (fp32, zero-initialised) += sum over pixels
+#define ST_DP32 132                   // dY^T row pitch (128 pixels + 4): == 4 (mod 32)
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_wgrad_tf32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw_acc,
+                       int N, int H, int W, int OH, int OW)
+{
+    __shared__ __align__(16) float s_patch[ST_PATCH_ELEMS];
+    __shared__ __align__(16) float s_dyT[ST_CO * ST_DP32];       // [co][pixel ^ swz(co)]
+    __shared__ int16_t s_koff[ST_KP];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    fill_koff(s_koff);
+
+    // warp -> (m-tile of 16 output channels, 10 consecutive n-tiles of 8 k-indices)
+    const int mt = warp & 3, nt0 = (warp >> 2) * 10;
+    float acc[10][4];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+
+    const int tiles_w = (OW + ST_TW - 1) / ST_TW, tiles_h = (OH + ST_TH - 1) / ST_TH;
+    const long long n_tiles = (long long)N * tiles_h * tiles_w;
+
+    // register prefetch of the NEXT tile: input patch + the 8 x 16 B of dy this thread stages
+    float pre[ST_PATCH_PER_THREAD];
+    float4 dpre[8];
+    auto dy_fetch = [&](TileCoord tc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + i * ST_THREADS;
+            const int p = e >> 4, part = e & 15;                  // 16 x 16 B per pixel
+            const int oh = tc.oh0 + p / ST_TW, ow = tc.ow0 + p % ST_TW;
+            dpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oh < OH && ow < OW)
+                dpre[i] = __ldg(reinterpret_cast<const float4*>(
+                    dy + (((size_t)tc.n * OH + oh) * OW + ow) * ST_CO + part * 4));
+        }
+    };
+    if ((long long)blockIdx.x < n_tiles) {
+        const TileCoord tc0 = tile_coord(blockIdx.x, tiles_h, tiles_w);
+        patch_fetch_f32(pre, x, tc0, H, W);
+        dy_fetch(tc0);
+    }
+
+    // A-fragment rows of this warp: co = mt*16 + gid (swizzle 2*mt) and co + 8 (swizzle 2*mt + 1)
+    const int swz_lo = (mt * 2) & 7, swz_hi = (mt * 2 + 1) & 7;
+    const float* d_lo = s_dyT + (mt * 16 + gid) * ST_DP32;
+    const float* d_hi = d_lo + 8 * ST_DP32;
+
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        __syncthreads();
+        patch_commit_f32(s_patch, pre);
+        // dy tile transposed to [co][pixel]; the pixel index is XOR-swizzled with (co >> 3) & 7 so
+        // that the 16 lanes that write 16 different channel quads of one pixel hit 16 banks
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + i * ST_THREADS;
+            const int p = e >> 4, part = e & 15;
+            const float v[4] = {dpre[i].x, dpre[i].y, dpre[i].z, dpre[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int co = part * 4 + q;
+                s_dyT[co * ST_DP32 + (p ^ ((co >> 3) & 7))] = v[q];
+            }
+        }
+        __syncthreads();
+        if (t + gridDim.x < n_tiles) {
+            const TileCoord tn = tile_coord(t + gridDim.x, tiles_h, tiles_w);
+            patch_fetch_f32(pre, x, tn, H, W);
+            dy_fetch(tn);
+        }
+
+        // GEMM K dimension = the tile's 128 pixels, 8 per step (half an output row per step)
+#pragma unroll 1
+        for (int ks = 0; ks < 2 * ST_TH; ++ks) {
+            const int pix = ks * 8 + tig;                        // pixel of a0/a1/b0; +4: a2/a3/b1
+            uint32_t a[4];
+            a[0] = __float_as_uint(d_lo[pix ^ swz_lo]);
+            a[1] = __float_as_uint(d_hi[pix ^ swz_hi]);
+            a[2] = __float_as_uint(d_lo[(pix + 4) ^ swz_lo]);
+            a[3] = __float_as_uint(d_hi[(pix + 4) ^ swz_hi]);
+            // im2col rows of pixels (pr, pc) and (pr, pc + 4)
+            const int pb0 = (2 * (ks >> 1)) * ST_PITCH + 6 * ((ks & 1) * 8 + tig), pb1 = pb0 + 24;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const int o = s_koff[(nt0 + j) * 8 + gid];
+                uint32_t b[2];
+                if (o >= 0) {
+                    b[0] = __float_as_uint(s_patch[pb0 + o]);
+                    b[1] = __float_as_uint(s_patch[pb1 + o]);
+                } else {
+                    b[0] = b[1] = 0u;
+                }
+                mma_tf32_1688(acc[j], a, b);
+            }
+        }
+    }
+
+    // one atomic per accumulator element: rows = output channel, cols = k index
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int k = (nt0 + j) * 8 + tig * 2;
+        const int co = mt * 16 + gid;
+        if (k < ST_K)     { atomicAdd(dw_acc + co * ST_K + k, acc[j][0]);
+                            atomicAdd(dw_acc + (co + 8) * ST_K + k, acc[j][2]); }
+        if (k + 1 < ST_K) { atomicAdd(dw_acc + co * ST_K + k + 1, acc[j][1]);
+                            atomicAdd(dw_acc + (co + 8) * ST_K + k + 1, acc[j][3]); }
+    }
+}
+
 extern "C" {
+
+cudaError_t stem_launch_fwd_f32(const void* x, const void* w, void* y, int N, int H, int W, int OH, int OW,
+                                cudaStream_t st)
+{
+    const long long tiles = (long long)N * ((OH + ST_TH - 1) / ST_TH) * ((OW + ST_TW - 1) / ST_TW);
+    int grid = 148 * 2;
+    if (tiles < grid) grid = (int)tiles;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ST_F32_FWD_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    stem_fwd_tf32_kernel<<<grid, ST_THREADS, ST_F32_FWD_SMEM, st>>>((const float*)x, (const float*)w, (float*)y,
+                                                                    N, H, W, OH, OW);
+    return cudaGetLastError();
+}
+
+cudaError_t stem_launch_wgrad_f32(const void* x, const void* dy, float* dw_acc, int N, int H, int W,
+                                  int OH, int OW, cudaStream_t st)
+{
+    const long long tiles = (long long)N * ((OH + ST_TH - 1) / ST_TH) * ((OW + ST_TW - 1) / ST_TW);
+    int grid = 148 * 2;
+    if (tiles < grid) grid = (int)tiles;
+    stem_wgrad_tf32_kernel<<<grid, ST_THREADS, 0, st>>>((const float*)x, (const float*)dy, dw_acc, N, H, W, OH, OW);
+    return cudaGetLastError();
+}
 
 cudaError_t stem_launch_fwd(const void* x, const void* w, void* y, int N, int H, int W, int OH, int OW,
                             cudaStream_t st)

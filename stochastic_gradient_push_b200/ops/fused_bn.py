@@ -45,6 +45,10 @@ FORCE_REFERENCE = False      # debugging / A-B switch: route everything to the P
 USE_TCGEN05_CONV1X1 = os.environ.get('SGP_B200_CONV1X1', '1') != '0'
 
 
+# the tensor-core stem kernels (csrc/stem_kernels.cu); SGP_B200_STEM=0 -> library convolution
+USE_STEM_KERNELS = os.environ.get('SGP_B200_STEM', '1') != '0'
+
+
 def _can_fuse(x: torch.Tensor) -> bool:
     if FORCE_REFERENCE or not x.is_cuda or not native.available():
         return False
@@ -137,7 +141,7 @@ class _Conv1x1BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu):
         C = native.load()
-        w16 = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        w16 = w if w.dtype == x.dtype else w.detach().to(x.dtype)      # compute-dtype weights
         yraw, out, coef = C.conv1x1_bn_forward(x, w16, residual, gamma, beta, running_mean, running_var,
                                                nbt, momentum, eps, relu)
         ctx.relu = relu
@@ -172,7 +176,7 @@ class _Conv1x1BNActSplit(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu):
         C = native.load()
-        w16 = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        w16 = w if w.dtype == x.dtype else w.detach().to(x.dtype)
         yraw, out, coef = C.conv1x1_bn_forward(x, w16, None, gamma, beta, running_mean, running_var,
                                                nbt, momentum, eps, relu)
         ctx.relu = relu
@@ -193,9 +197,9 @@ class _Conv1x1BNActSplit(torch.autograd.Function):
             # dX = dY . W: the same GEMM with the transposed weight as its K-major B operand
             wt = w16.reshape(w16.shape[0], w16.shape[1]).t().contiguous()
             res = d_skip
-            if res is not None and (res.dtype != torch.bfloat16
+            if res is not None and (res.dtype != dyraw.dtype
                                     or not res.is_contiguous(memory_format=torch.channels_last)):
-                res = res.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                res = res.to(dyraw.dtype).contiguous(memory_format=torch.channels_last)
             if C.conv1x1_can_fuse(dyraw, wt):
                 dx = C.conv1x1_forward(dyraw, wt, False, res)
             else:
@@ -223,12 +227,17 @@ def _conv1x1_operands(conv, bn, x, residual, relu):
     w = conv.weight
     if x.dtype == torch.float32 and torch.is_autocast_enabled():
         x = x.to(torch.bfloat16)
-    if not (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
-            and (w.dtype == torch.bfloat16 or torch.is_autocast_enabled())
-            and (residual is None or (residual.dtype == torch.bfloat16
+    if x.dtype == torch.float32:
+        # fp32 activations: the GEMM multiplies in TF32 (what the library convolution does by
+        # default); honour a user who switched TF32 off
+        dtype_ok = w.dtype == torch.float32 and torch.backends.cudnn.allow_tf32
+    else:
+        dtype_ok = x.dtype == torch.bfloat16 and (w.dtype == torch.bfloat16 or torch.is_autocast_enabled())
+    if not (dtype_ok and x.is_contiguous(memory_format=torch.channels_last)
+            and (residual is None or (residual.dtype == x.dtype
                                       and residual.is_contiguous(memory_format=torch.channels_last)))):
         return x, False
-    wk = w if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+    wk = w if w.dtype == x.dtype else w.detach().to(x.dtype)
     return x, bool(native.load().conv1x1_can_fuse(x, wk)) and conv.out_channels % 8 == 0
 
 
@@ -300,9 +309,9 @@ class _StemConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         C = native.load()
-        w16 = weight
-        if w16.dtype != torch.bfloat16 or not w16.is_contiguous(memory_format=torch.channels_last):
-            w16 = weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w16 = weight                   # compute-dtype weights: bf16, or fp32 (TF32 tensor-core math)
+        if w16.dtype != x.dtype or not w16.is_contiguous(memory_format=torch.channels_last):
+            w16 = weight.detach().to(x.dtype).contiguous(memory_format=torch.channels_last)
         ctx.save_for_backward(x)
         ctx.w_dtype = weight.dtype
         return C.stem_forward(x, w16)
@@ -320,13 +329,15 @@ def stem_conv(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     NHWC bf16 CUDA inputs run the tensor-core implicit-GEMM kernels in
     ``csrc/stem_kernels.cu`` (the library needs 1.48 ms + 0.77 ms for this layer at batch
     256; its HBM traffic is worth ~0.1 ms); anything else runs ``conv`` unchanged."""
-    ok = (not FORCE_REFERENCE and x.is_cuda and native.available() and not x.requires_grad
+    ok = (USE_STEM_KERNELS and not FORCE_REFERENCE and x.is_cuda and native.available() and not x.requires_grad
           and conv.in_channels == 3 and conv.out_channels == 64 and conv.kernel_size == (7, 7)
           and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.dilation == (1, 1)
           and conv.groups == 1 and conv.bias is None)
     if ok and x.dtype == torch.float32 and torch.is_autocast_enabled():
         x = x.to(torch.bfloat16)          # what autocast would do inside the convolution
-    if ok and x.dtype == torch.bfloat16 and x.dim() == 4 \
+    dtype_ok = x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and conv.weight.dtype == torch.float32
+                                             and torch.backends.cudnn.allow_tf32)
+    if ok and dtype_ok and x.dim() == 4 \
             and x.is_contiguous(memory_format=torch.channels_last) and x.shape[2] >= 7 and x.shape[3] >= 7:
         return _StemConv.apply(x, conv.weight)
     return conv(x)

@@ -96,8 +96,13 @@ class GossipEngine(object):
         self._state_i32 = self.state.view(torch.int32)
         self._state_f32[C.STATE_OFF_PSW // 4: C.STATE_OFF_PSW // 4 + 2] = 1.0
         self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32).pin_memory()
+        # ring of pinned staging rows: an lr change must not rewrite host memory that an earlier,
+        # still-queued async H2D copy is going to read
+        self._hyper_host = torch.zeros(8, C.HYPER_FLOATS, dtype=torch.float32).pin_memory()
+        self._hyper_slot = 0
+        self._hyper_events = [None] * 8
         self._hyper_cache = None
+        self._status_host = None
 
         table, wtable = build_tables(graph, mixing, self.device)
         self.ctx = C.GossipContext(
@@ -132,12 +137,19 @@ class GossipEngine(object):
         if key == self._hyper_cache:
             return
         self._hyper_cache = key
-        h = self._hyper_host
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % self._hyper_host.shape[0]
+        ev = self._hyper_events[slot]
+        if ev is not None:
+            ev.synchronize()                 # the copy that last used this row has executed
+        h = self._hyper_host[slot]
         h[0], h[1], h[2] = key[0], key[1], key[2]
         h[3] = 1.0 if key[3] else 0.0
         h[4] = 1.0 if key[4] else 0.0
         h[5] = key[5]
         self.hyper.copy_(h, non_blocking=True)
+        ev = self._hyper_events[slot] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
 
     def set_schedule(self, graph=None, mixing=None):
         """Re-emit the device tables (e.g. after ``peers_per_itr`` changed).
@@ -237,6 +249,34 @@ class GossipEngine(object):
     @property
     def status(self) -> int:
         return int(self._state_i32[self.C.STATE_OFF_STATUS // 4].item())
+
+    def poll(self, blocking: bool = False):
+        """Heartbeat poll of the kernels' sticky status word.  Non-blocking: enqueue a 4-byte
+        async copy of the word into pinned host memory on the current stream and look at the
+        value the PREVIOUS poll delivered (no host synchronisation; a failure is reported one
+        poll late).  ``blocking=True`` synchronises the stream first.  Raises
+        ``NameError('Gossip flag timeout')`` -- the reference's heartbeat error
+        (``gossip/distributed.py:349-352``)."""
+        if self._status_host is None:
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._status_dev = self._state_i32[self.C.STATE_OFF_STATUS // 4:
+                                               self.C.STATE_OFF_STATUS // 4 + 1]
+        if torch.cuda.is_current_stream_capturing():
+            return
+        st = int(self._status_host[0])
+        if st == 0:
+            self._status_host.copy_(self._status_dev, non_blocking=True)
+            if blocking:
+                torch.cuda.current_stream(self.device).synchronize()
+                st = int(self._status_host[0])
+        if st != 0:
+            raise NameError('Gossip flag timeout (rank %d: %s)' % (self.rank, self._status_name(st)))
+
+    @staticmethod
+    def _status_name(st):
+        return {1: 'in-neighbour never published (heartbeat timeout)',
+                2: 'out-neighbour never released the outbox (ack timeout)',
+                3: 'device barrier timeout'}.get(st, 'code %d' % st)
 
     def check(self):
         st = self.status

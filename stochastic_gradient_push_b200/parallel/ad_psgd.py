@@ -145,9 +145,11 @@ class BilatGossipDataParallel(Module):
 
         use_kernels = False
         if transport == 'auto':
-            from .distributed import _native_ok
+            from .distributed import _native_ok, _single_nvlink_domain
             use_kernels = on_cuda and not self.__cpu_comm and first.dtype == torch.float32 \
                 and _native_ok()
+            # kernels need one NVLink domain (all ranks on one host); else the c10d loop
+            use_kernels = _single_nvlink_domain(world_size, use_kernels)
         elif transport in ('nvlink', 'kernel', 'peer'):
             use_kernels = True
         self.transport = 'nvlink' if use_kernels else 'c10d'
@@ -382,6 +384,7 @@ class BilatGossipDataParallel(Module):
         rnd = 0
         sent = None
         inflight = []
+        wait = self._poll
         t_round = time.time()
 
         def key(r, src, dst):
@@ -407,9 +410,18 @@ class BilatGossipDataParallel(Module):
                 if not passive:
                     sent = publish()
             in_edge = g.in_edges[0]
-            if not store.check([key(rnd, in_edge.src, in_edge.dest)]):
-                time.sleep(self._poll)
+            in_key = key(rnd, in_edge.src, in_edge.dest)
+            if not store.check([in_key]):
+                # back off exponentially (x1.5 up to 20 ms): a quiet partner must not cost the
+                # store on rank 0 a constant 5 kHz of polls from every rank
+                time.sleep(wait)
+                wait = min(wait * 1.5, 0.02)
                 continue
+            wait = self._poll
+            try:
+                store.delete_key(in_key)       # consumed: the store does not grow with the run
+            except Exception:                  # (a store without delete support keeps the key)
+                pass
             if sent is None:          # passive: answer now that the partner showed up
                 sent = publish()
             tr.post_recvs([g.in_msg_buffer], [in_edge])[0].wait()

@@ -122,6 +122,8 @@ class _EngineShim(object):
         self.ar = ar
         self.device = ar.device
         self.steps = 0
+        from ..ops import native
+        self.C = native.load()
 
     def set_hyper(self, lr, momentum, weight_decay, nesterov, do_sgd=True, grad_scale=1.0):
         self.ar.set_hyper(lr, momentum, weight_decay, nesterov, grad_scale)
@@ -146,7 +148,9 @@ class ARTrainer(GossipTrainer):
         self.opt = _Opt()
         self.engine = _EngineShim(model)
         self.k = None
-        self.criterion = criterion or torch.nn.CrossEntropyLoss()
+        from ..ops.fused_loss import FusedCrossEntropyWithAccuracy
+        self.criterion = criterion or FusedCrossEntropyWithAccuracy()
+        self._fused_loss = isinstance(self.criterion, FusedCrossEntropyWithAccuracy)
         self.amp_dtype = amp_dtype
         self.use_graph = use_cuda_graph
         self.warmup_iters = warmup_iters
@@ -156,6 +160,7 @@ class ARTrainer(GossipTrainer):
         self.gossip = False
         self.graph = None
         self.static_in = self.static_tgt = self.static_loss = self.static_out = None
+        self.static_metrics = None
         self._eager_steps = 0
         self.stream = torch.cuda.Stream(device=self.device)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -166,6 +171,8 @@ class ARTrainer(GossipTrainer):
         self._prefetched = False
         self._loss_ring = None
         self._loss_slot = 0
+        self._skip_next_sgd = False
+        self.own_launches_per_step = None
 
     def _one_step(self, first=False):
         self._fwd_bwd()
@@ -176,4 +183,7 @@ class ARTrainer(GossipTrainer):
 
     def finish(self):
         torch.cuda.synchronize(self.device)
+        self.ar.check()
+
+    def check(self):
         self.ar.check()

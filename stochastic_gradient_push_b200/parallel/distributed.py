@@ -168,12 +168,22 @@ class _C10dBackend(object):
             _wait_req(reqs, i, deadline)
         w_res = 0.0
         first = True
+        staged = False
         for arena, bufs in recvs:
             for b in bufs:
+                staged = staged or (b.device != arena.flat.device)
                 arena.flat.add_(b[:-1].to(arena.flat.device, non_blocking=True))
                 if first:
                     w_res += float(b[-1])
             first = False
+        if staged and torch.cuda.is_available():
+            # pinned CPU receive buffers -> GPU arena: the async H2D copies read the buffers when
+            # the STREAM reaches them.  start() re-posts irecvs into the same buffers right away
+            # (overlap mode: finish and start run back to back), so a peer's next message could
+            # land before the DMA of this round has run.  Wait for the copies first.
+            for arena, _ in recvs:
+                if arena.flat.is_cuda:
+                    torch.cuda.current_stream(arena.flat.device).synchronize()
         self.pending = None
         return w_res
 
@@ -308,6 +318,14 @@ class GossipDataParallel(Module):
         all_fp32 = list(by_dtype.keys()) == [torch.float32]
         if transport == 'auto':
             use_kernels = on_cuda and not self.__cpu_comm and all_fp32 and _native_ok()
+            # the kernel data plane maps every peer's buffers over CUDA IPC / NVSwitch: it needs
+            # ALL ranks on one host (one NVLink domain) and at most MAX_RANKS of them.  Anything
+            # else (the multi-node SLURM scripts) falls back to the c10d data plane.
+            if not _single_nvlink_domain(world_size * self.nprocs_per_node, use_kernels):
+                if use_kernels:
+                    self.logger.info('ranks span several hosts (or > %d ranks): using the c10d '
+                                     'transport instead of the NVLink kernels' % _max_kernel_ranks())
+                use_kernels = False
         else:
             use_kernels = transport in ('nvlink', 'kernel', 'peer')
         if use_kernels and not (on_cuda and all_fp32):
@@ -343,7 +361,9 @@ class GossipDataParallel(Module):
         # hierarchical mode: the node masters rendezvous among themselves; new_group is
         # collective over the WHOLE world, so every rank creates it
         self._masters_group = None
-        if self.nprocs_per_node > 1 and use_kernels and world_size > 1 and dist.is_initialized():
+        if self.nprocs_per_node > 1 and world_size > 1 and dist.is_initialized():
+            # (both data planes: the kernel rendezvous and the bounded-staleness drain of the
+            # c10d plane are collectives among the node masters only)
             self._masters_group = dist.new_group(
                 [r * self.nprocs_per_node for r in range(world_size)])
         if self.is_local_master:
@@ -574,7 +594,8 @@ class GossipDataParallel(Module):
             return
         dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
         flag = torch.zeros(1, device=dev)
-        left_loop = dist.all_reduce(flag, async_op=True)
+        grp = self._masters_group       # None (= world) unless nprocs_per_node > 1: only masters gossip
+        left_loop = dist.all_reduce(flag, async_op=True, group=grp)
         t0 = time.time()
         while not left_loop.is_completed():
             if self._query_gossip_queue(non_blocking=True) is not False or not self.gossiping:
@@ -584,7 +605,7 @@ class GossipDataParallel(Module):
                 raise NameError('Gossip flag timeout')
         left_loop.wait()
         t = torch.tensor([self._rounds_started], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=grp)
         target = int(t.item())
         while True:
             self._query_gossip_queue(non_blocking=False)
@@ -605,6 +626,10 @@ class GossipDataParallel(Module):
 
         if self._kernel is not None:
             k = self._kernel
+            # heartbeat: one 4-byte async read-back of the kernels' sticky status word per query;
+            # raises NameError('Gossip flag timeout') like the reference (:349-352) as soon as a
+            # timed-out wait has been observed (non-blocking: sees the previous launches' state)
+            k.engine.poll(blocking=not non_blocking and self.overlap)
             if self.overlap and k.gather_event is not None:
                 if non_blocking and not k.gather_event.query():
                     return False
@@ -692,6 +717,8 @@ class GossipDataParallel(Module):
                            in_numerator=self.is_ps_numerator)
             k.residual_pending = False
             self.is_ps_numerator = False
+        # drain points (state_dict / sync_comms / eval / schedule change): a blocking health check
+        k.engine.poll(blocking=True)
 
     # -- hooks ----------------------------------------------------------------- #
     def __register_hooks(self):
@@ -734,6 +761,25 @@ class GossipDataParallel(Module):
 def _native_ok() -> bool:
     from ..ops import native
     return torch.cuda.is_available() and native.available()
+
+
+def _max_kernel_ranks() -> int:
+    from ..ops import native
+    return int(native.load().MAX_RANKS) if native.available() else 0
+
+
+def _single_nvlink_domain(total_ranks: int, local_ok: bool) -> bool:
+    """Collective (when torch.distributed is up): True iff every rank wants the kernel transport,
+    all ranks run on one host and there are at most MAX_RANKS of them.  Every rank must call it
+    with the same arguments' meaning, so that all of them pick the same data plane."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return bool(local_ok)
+    import socket
+    info = (socket.gethostname(), bool(local_ok))
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, info)
+    hosts = set(h for h, _ in gathered)
+    return all(ok for _, ok in gathered) and len(hosts) == 1 and len(gathered) <= _max_kernel_ranks()
 
 
 class _GossiperView(object):

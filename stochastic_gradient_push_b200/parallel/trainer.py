@@ -28,6 +28,7 @@ from typing import Callable, Optional
 
 import torch
 
+from ..ops.fused_loss import FusedCrossEntropyWithAccuracy
 from ..optim import FusedGossipSGD
 from .distributed import GossipDataParallel
 
@@ -43,7 +44,10 @@ class GossipTrainer(object):
         self.opt = optimizer
         self.engine = model._kernel.engine
         self.k = model._kernel
-        self.criterion = criterion or torch.nn.CrossEntropyLoss()
+        # default: fused softmax cross-entropy that also yields prec@1 / prec@5 (the reference loop
+        # measures both every iteration, gossip_sgd.py:394-399) in the same launch
+        self.criterion = criterion or FusedCrossEntropyWithAccuracy()
+        self._fused_loss = isinstance(self.criterion, FusedCrossEntropyWithAccuracy)
         self.amp_dtype = amp_dtype
         self.use_graph = use_cuda_graph
         self.warmup_iters = warmup_iters
@@ -55,6 +59,7 @@ class GossipTrainer(object):
         self.static_in = None
         self.static_tgt = None
         self.static_loss = None
+        self.static_metrics = None
         self.static_out = None
         self._eager_steps = 0
         # see _backward(); SGP_B200_BATCHED_GRAD_COPY=0 restores per-parameter accumulation
@@ -72,6 +77,10 @@ class GossipTrainer(object):
         self._prefetched = False
         self._loss_ring = None
         self._loss_slot = 0
+        self._skip_next_sgd = False
+        # kernels of OUR extension in one training step (counted over the graph capture, or over
+        # the last eager step): what bench.py reports as gpu_launches / step
+        self.own_launches_per_step = None
 
     # ------------------------------------------------------------------ #
     def _autocast(self):
@@ -87,13 +96,17 @@ class GossipTrainer(object):
             net = twin[0]
             net.train(self.model.module.training)
             out = net(self.static_in)
-            loss = self.criterion(out.float(), self.static_tgt)
+            loss = self.criterion(out if self._fused_loss else out.float(), self.static_tgt)
         else:
             with self._autocast():
                 out = self.model.module(self.static_in)
-                loss = self.criterion(out.float(), self.static_tgt)
+                loss = self.criterion(out if self._fused_loss else out.float(), self.static_tgt)
         self._backward(loss, net if twin else self.model.module)
-        self.static_loss.copy_(loss.detach())
+        metrics = getattr(self.criterion, 'metrics', None)
+        if metrics is not None:
+            self.static_metrics.copy_(metrics)          # [loss, prec@1 %, prec@5 %]
+        else:
+            self.static_metrics[0].copy_(loss.detach())
         self.static_out = out.detach()
 
     def _backward(self, loss, net):
@@ -172,15 +185,22 @@ class GossipTrainer(object):
         # stage -> static copy performs the NCHW -> NHWC permute
         self._stage = torch.empty(batch.shape, dtype=batch.dtype, device=self.device)
         self._stage_tgt = torch.empty_like(self.static_tgt)
-        self.static_loss = torch.zeros((), dtype=torch.float32, device=self.device)
-        self._loss_ring = torch.zeros(1024, dtype=torch.float32).pin_memory()
+        self.static_metrics = torch.full((3,), float('nan'), dtype=torch.float32, device=self.device)
+        self.static_loss = self.static_metrics[0]
+        self._metrics_ring = torch.zeros(1024, 3, dtype=torch.float32).pin_memory()
+        self._loss_ring = self._metrics_ring[:, 0]
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self._stage_free.record(self.stream)
 
     def _set_lr(self):
         g = self.opt.param_groups[0]
+        # overlap: the SGD of step k runs inside publish(k+1).  After finish() applied it early
+        # (end of epoch / checkpoint) the next replay's publish must not apply it again: the
+        # captured kernel reads `do_sgd` from device memory
+        do_sgd = not self._skip_next_sgd
+        self._skip_next_sgd = False
         self.engine.set_hyper(g['lr'], g['momentum'], g['weight_decay'], g['nesterov'],
-                              do_sgd=True, grad_scale=self.opt.grad_scale)
+                              do_sgd=do_sgd, grad_scale=self.opt.grad_scale)
 
     def prefetch(self, batch_cpu, target_cpu):
         """Start the H2D copy of the NEXT step's inputs on the copy stream."""
@@ -214,7 +234,8 @@ class GossipTrainer(object):
         the FOLLOWING step; their H2D copy is started on the prefetch stream as
         soon as this step's inputs have left the staging buffer, so it overlaps
         this step's compute.  Returns the slot of :attr:`loss_ring` that holds
-        this step's loss once the stream has drained (no host sync here)."""
+        this step's loss -- and of :attr:`metrics_ring` that holds ``[loss, prec@1 %, prec@5 %]``
+        -- once the stream has drained (no host sync here)."""
         if batch is not None:
             self._ensure_static(batch, target)
         self._load_inputs(batch, target)
@@ -224,8 +245,8 @@ class GossipTrainer(object):
         slot = self._loss_slot
         if read_loss:
             with torch.cuda.stream(self.stream):
-                self._loss_ring[slot:slot + 1].copy_(self.static_loss.view(1), non_blocking=True)
-            self._loss_slot = (slot + 1) % self._loss_ring.numel()
+                self._metrics_ring[slot].copy_(self.static_metrics, non_blocking=True)   # 12 bytes D2H
+            self._loss_slot = (slot + 1) % self._metrics_ring.shape[0]
         return slot
 
     def step_resident(self):
@@ -248,7 +269,9 @@ class GossipTrainer(object):
             self.graph.replay()
             self._after_replay()
         else:
+            c0 = self.engine.C.launch_count()
             self._one_step(first=(self._eager_steps == 0))
+            self.own_launches_per_step = self.engine.C.launch_count() - c0
             self._eager_steps += 1
 
     def _after_replay(self):
@@ -259,20 +282,38 @@ class GossipTrainer(object):
     def loss_ring(self):
         return self._loss_ring
 
+    @property
+    def metrics_ring(self):
+        """pinned ``[1024, 3]`` ring: row ``slot`` = ``[loss, prec@1 %, prec@5 %]`` of that step"""
+        return self._metrics_ring
+
     def _capture(self):
         torch.cuda.synchronize(self.device)
         steps_before = self.engine.steps
         self.graph = torch.cuda.CUDAGraph()
+        c0 = self.engine.C.launch_count()
         with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode='thread_local'):
             self._one_step(first=False)
+        self.own_launches_per_step = self.engine.C.launch_count() - c0
         # capture does not execute: undo the host-side step mirror advance
         self.engine.steps = steps_before
         torch.cuda.synchronize(self.device)
 
     def finish(self):
-        """Drain: apply the last deferred SGD / residual (overlap) and sync."""
-        if self.overlap and self.gossip:
+        """Drain: apply the last deferred SGD / residual (overlap), sync, and poll the kernels'
+        health word.  Call at the end of an epoch, before validation / ``state_dict()``: the
+        parameters then hold every update and all the push-sum mass received so far.  Training
+        may simply continue afterwards (the next step skips the SGD that was applied here)."""
+        if self.overlap and self.gossip and self._eager_steps + (self.graph is not None) > 0:
             with torch.cuda.stream(self.stream):
+                self.stream.wait_stream(self.model.gossip_stream)
+                self._set_lr()
                 self.engine.local(sgd=True, fold=True)
+                self.engine.residual.zero_()       # already folded: the next publish adds 0
+            self._skip_next_sgd = True
         torch.cuda.synchronize(self.device)
+        self.engine.check()
+
+    def check(self):
+        """Raise if a gossip kernel reported a heartbeat / ack timeout (reads one word)."""
         self.engine.check()

@@ -16,11 +16,74 @@ GEMM_SHAPES = [(128, 64, 64), (677, 64, 64), (1000, 256, 128), (4096, 128, 256),
                (130, 192, 1024), (4224, 256, 256), (2000, 1024, 64), (25088, 64, 256), (6272, 1024, 256), (1568, 2048, 512), (40000, 72, 192)]
 
 
-def _mats(M, K, N, x_mean=0.0):
+def _mats(M, K, N, x_mean=0.0, dtype=torch.bfloat16):
     g = torch.Generator(device='cuda').manual_seed(M + K + N)
-    x = (torch.randn(M, K, device='cuda', generator=g) + x_mean).to(torch.bfloat16)
-    w = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).to(torch.bfloat16)
+    x = (torch.randn(M, K, device='cuda', generator=g) + x_mean).to(dtype)
+    w = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).to(dtype)
     return x, w
+
+
+def _tf32(t):
+    """what kind::tf32 sees of an fp32 operand: the top 19 bits (sign, 8 exponent, 10 mantissa)"""
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+# fp32 operands (K % 4 == 0 suffices: 16-byte rows), TF32 tensor-core math, fp32 output
+GEMM_SHAPES_F32 = GEMM_SHAPES + [(515, 36, 64), (300, 100, 128)]
+
+
+@pytest.mark.parametrize('M,K,N', GEMM_SHAPES_F32)
+def test_tf32_gemm_matches_fp32_matmul(M, K, N):
+    """kind::tf32 path: against an fp64 matmul of the tf32-truncated operands (tight) and of the
+    full fp32 operands (TF32-level tolerance, the precision of the reference's cuDNN convs)."""
+    C = native.load()
+    x, w = _mats(M, K, N, dtype=torch.float32)
+    assert C.conv1x1_can_fuse(x, w)
+    y = C.conv1x1_forward(x, w)
+    torch.cuda.synchronize()
+    assert y.shape == (M, N) and y.dtype == torch.float32
+    exact = (_tf32(x).double() @ _tf32(w).double().t()).float()
+    torch.testing.assert_close(y, exact, rtol=2e-5, atol=2e-5 * K ** 0.5)
+    want = (x.double() @ w.double().t()).float()
+    torch.testing.assert_close(y, want, rtol=5e-3, atol=5e-3)
+
+
+@pytest.mark.parametrize('M,K,N', GEMM_SHAPES_F32)
+@pytest.mark.parametrize('x_mean', [0.0, 3.0])
+def test_tf32_fused_statistics_match_two_pass(M, K, N, x_mean):
+    C = native.load()
+    x, w = _mats(M, K, N, x_mean, dtype=torch.float32)
+    if x_mean:
+        w = w + 0.05
+    gamma = torch.rand(N, device='cuda') + 0.5
+    beta = torch.randn(N, device='cuda') * 0.1
+    rm, rv = torch.zeros(N, device='cuda'), torch.ones(N, device='cuda')
+    nbt = torch.zeros((), dtype=torch.long, device='cuda')
+    yraw, out, coef = C.conv1x1_bn_forward(x, w, None, gamma, beta, rm, rv, nbt, 0.1, 1e-5, True)
+    torch.cuda.synchronize()
+    assert yraw.dtype == torch.float32 and out.dtype == torch.float32
+    exact = (_tf32(x).double() @ _tf32(w).double().t())
+    torch.testing.assert_close(yraw.double(), exact, rtol=2e-5, atol=2e-5 * K ** 0.5 * max(1.0, x_mean * 4))
+    yd = yraw.double()
+    mean, var = yd.mean(0), yd.var(0, unbiased=False)
+    torch.testing.assert_close(coef[0].double(), mean, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(coef[1].double(), (var + 1e-5).rsqrt(), rtol=2e-4, atol=1e-5)
+    want = F.relu(F.batch_norm(yraw, None, None, gamma, beta, True, 0.1, 1e-5))
+    torch.testing.assert_close(out, want, rtol=1e-3, atol=1e-3)
+    assert int(nbt) == 1
+    torch.testing.assert_close(rm.double(), 0.1 * mean, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('M,K,N', GEMM_SHAPES_F32)
+def test_tf32_gemm_residual_epilogue(M, K, N):
+    C = native.load()
+    x, w = _mats(M, K, N, dtype=torch.float32)
+    g = torch.Generator(device='cuda').manual_seed(7)
+    r = torch.randn(M, N, device='cuda', generator=g) * 2
+    y = C.conv1x1_forward(x, w, False, r)
+    torch.cuda.synchronize()
+    exact = (_tf32(x).double() @ _tf32(w).double().t() + r.double()).float()
+    torch.testing.assert_close(y, exact, rtol=2e-5, atol=2e-5 * K ** 0.5)
 
 
 @pytest.mark.parametrize('M,K,N', GEMM_SHAPES)
@@ -152,6 +215,54 @@ def test_unsupported_inputs_fall_back(monkeypatch):
     bn.eval()
     y = conv_bn_act(conv, bn, x.contiguous(memory_format=torch.channels_last), relu=True)
     assert y.shape == (2, 128, 8, 8)
+
+
+@pytest.mark.parametrize('cin,width,hw', [(256, 64, 14), (512, 128, 7)])
+def test_fp32_bottleneck_matches_library_path(monkeypatch, cin, width, hw):
+    """fp32 activations / weights (the precision-matched flagship path): a bottleneck through the
+    TF32 tcgen05 GEMMs (statistics + skip gradient fused) and through library TF32 convolutions +
+    the stand-alone fused BN, both measured against the SAME block evaluated in fp64.  TF32
+    rounding flips ReLU masks of near-zero activations, so two TF32 paths differ element-wise;
+    what must hold is that ours is as close to the fp64 truth as the library path is."""
+    import copy
+    from stochastic_gradient_push_b200.models.resnet import Bottleneck
+    torch.manual_seed(5)
+    blk0 = Bottleneck(cin, width, 1, None).cuda().to(memory_format=torch.channels_last)
+    with torch.no_grad():
+        for m in blk0.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.1)
+    g = torch.Generator(device='cuda').manual_seed(2)
+    xin = torch.randn(8, cin, hw, hw, device='cuda', generator=g).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(8, 4 * width, hw, hw, device='cuda', generator=g).contiguous(memory_format=torch.channels_last)
+
+    def run(mode):
+        blk = copy.deepcopy(blk0)
+        x0 = xin.clone()
+        d = dy
+        if mode == 'fp64':
+            blk, x0, d = blk.double(), x0.double(), dy.double()
+            monkeypatch.setattr(fused_bn, 'FORCE_REFERENCE', True)
+        else:
+            monkeypatch.setattr(fused_bn, 'FORCE_REFERENCE', False)
+            monkeypatch.setattr(fused_bn, 'USE_TCGEN05_CONV1X1', mode == 'ours')
+        x0.requires_grad_(True)
+        y = blk(x0 * 1)
+        y.backward(d)
+        torch.cuda.synchronize()
+        out = dict(y=y.detach().double(), dx=x0.grad.double())
+        out.update({n: p.grad.double() for n, p in blk.named_parameters()})
+        return out
+
+    truth, ours, lib = run('fp64'), run('ours'), run('lib')
+    monkeypatch.setattr(fused_bn, 'FORCE_REFERENCE', False)
+    for key in truth:
+        scale = truth[key].norm().item() + 1e-12
+        e_ours = (ours[key] - truth[key]).norm().item() / scale
+        e_lib = (lib[key] - truth[key]).norm().item() / scale
+        assert e_ours < max(3.0 * e_lib, 2e-3), (key, e_ours, e_lib)
+        assert e_ours < 2e-2, (key, e_ours)
 
 
 @pytest.mark.parametrize('cin,width,hw', [(256, 64, 14), (64, 64, 9), (512, 128, 7)])

@@ -26,8 +26,8 @@ def C():
         pytest.skip('native extension unavailable: %s' % e)
 
 
-def _check(C, M, N, K, sms, residual):
-    p = C.conv1x1_plan(M, N, K, sms, residual)
+def _check(C, M, N, K, sms, residual, f32=False):
+    p = C.conv1x1_plan(M, N, K, sms, residual, f32)
     bn = p['block_n']
     assert bn in (64, 128, 256) and N % bn == 0
     n_blocks = N // bn
@@ -40,8 +40,8 @@ def _check(C, M, N, K, sms, residual):
     assert p['store_slabs'] in (1, 2)
     if residual:
         assert p['store_slabs'] == 2                    # residual slabs are double-buffered
-    k_blocks = -(-K // 64)
-    b_bytes = bn * 64 * 2
+    k_blocks = -(-K // (32 if f32 else 64))     # a k-block is one 128-byte swizzle row
+    b_bytes = bn * 128
     stage = A_BYTES + (0 if p['resident_w'] else b_bytes)
     want = 1024 + 512 + (k_blocks * b_bytes if p['resident_w'] else 0) + p['stages'] * stage \
         + 8 * p['store_slabs'] * SLAB
@@ -62,6 +62,24 @@ def test_resnet50_layer_plans(C, residual):
     # K = 2048 cannot be resident; a narrower tile shortens the critical path on the 7x7 maps
     p = C.conv1x1_plan(12544, 512, 2048, 148, residual)
     assert not p['resident_w'] and p['block_n'] == 128
+
+
+def test_fp32_plans(C):
+    """fp32 / TF32 operands: k-blocks of 32 elements; the tile width is narrowed until the CTA's W
+    block stays resident when that is possible (fp32 W is twice as wide)."""
+    for M, N, K in RESNET50_SHAPES:
+        for residual in (False, True):
+            p = _check(C, M, N, K, 148, residual, f32=True)
+            assert p['grid'] >= 128, (M, N, K, p)
+    p = C.conv1x1_plan(802816, 256, 64, 148, False, True)
+    assert p['resident_w'] and p['block_n'] == 256          # 64 KB of W
+    p = C.conv1x1_plan(50176, 1024, 256, 148, False, True)
+    assert p['resident_w'] and p['block_n'] == 128          # 256-wide would be 256 KB
+    for M, N, K, sms, res in itertools.product((1, 129, 5000), (64, 192, 1024), (8, 36, 100, 1000),
+                                               (132, 148), (False, True)):
+        _check(C, M, N, K, sms, res, f32=True)
+    with pytest.raises(RuntimeError):
+        C.conv1x1_plan(128, 64, 10, 148, False, True)        # 40-byte rows
 
 
 def test_plan_invariants_over_a_shape_sweep(C):

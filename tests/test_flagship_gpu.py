@@ -33,6 +33,44 @@ def test_trainer_resnet50_loss_decreases_world1():
     assert all(l == l for l in losses)
 
 
+def test_trainer_fp32_tf32_path_matches_library_path(monkeypatch):
+    """The precision-matched flagship step (fp32 activations / weights, TF32 tcgen05 1x1 GEMMs with
+    fused statistics + skip gradient, TF32 stem kernels, fused loss + accuracy) against the same
+    step with every convolution on the library (cuDNN TF32): same losses within TF32 noise, both
+    memorise a fixed batch, metrics ring carries [loss, prec@1, prec@5]."""
+    import stochastic_gradient_push_b200 as sgp
+    from stochastic_gradient_push_b200 import models
+    from stochastic_gradient_push_b200.ops import fused_bn
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
+    dev = torch.device('cuda', 0)
+    x = torch.randn(8, 3, 96, 96, generator=torch.Generator().manual_seed(5)).pin_memory()
+    y = torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(6)).pin_memory()
+    runs = []
+    for own in (True, False):
+        monkeypatch.setattr(fused_bn, 'USE_TCGEN05_CONV1X1', own)
+        monkeypatch.setattr(fused_bn, 'USE_STEM_KERNELS', own)
+        torch.manual_seed(0)
+        net = models.init_imagenet_in_1hr(models.resnet50()).to(dev).to(memory_format=torch.channels_last)
+        model = GossipDataParallel(net, graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1),
+                                   rank=0, world_size=1, heartbeat_timeout=20)
+        opt = FusedGossipSGD(model, lr=0.02, momentum=0.9, weight_decay=1e-4, nesterov=True)
+        tr = GossipTrainer(model, opt, amp_dtype=None, use_cuda_graph=True, warmup_iters=2)
+        slots = [tr.step(x, y) for _ in range(10)]
+        tr.finish()
+        rows = [tr.metrics_ring[s].tolist() for s in slots]
+        assert tr.graph is not None and tr.own_launches_per_step > 100
+        runs.append(rows)
+    got, want = runs
+    for (l1, a1, b1), (l2, a2, b2) in zip(got[:4], want[:4]):
+        assert abs(l1 - l2) < 2e-2 * max(1.0, abs(l2)), (got, want)
+    for rows in runs:
+        assert rows[-1][0] < rows[0][0]
+        assert all(0.0 <= r[1] <= r[2] <= 100.0 for r in rows)
+    assert got[-1][1] >= 50.0          # the fixed batch of 8 is (mostly) memorised: prec@1 is live
+
+
 def test_allreduce_world1_matches_torch_sgd():
     from stochastic_gradient_push_b200.parallel.allreduce import AllReduceDataParallel
     dev = torch.device('cuda', 0)

@@ -212,6 +212,34 @@ def test_stem_conv_matches_conv2d(shape):
     assert (conv.weight.grad - wq.grad).abs().max().item() < 1e-2 * scale
 
 
+@pytest.mark.parametrize('shape', [(4, 3, 64, 64), (3, 3, 224, 224), (2, 3, 70, 90), (1, 3, 33, 47)])
+def test_stem_conv_tf32_matches_conv2d(shape):
+    """fp32 operands, TF32 tensor-core math (mma.sync.m16n8k8.tf32): forward and wgrad against an
+    fp64 convolution of the tf32-truncated operands (tight) and of the fp32 operands (TF32-level)."""
+    from stochastic_gradient_push_b200.ops.fused_bn import stem_conv
+
+    def tf32(t):
+        return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(shape, device='cuda').contiguous(memory_format=torch.channels_last)
+    y = stem_conv(conv, x)
+    assert y.dtype == torch.float32 and y.is_contiguous(memory_format=torch.channels_last)
+    assert y.grad_fn is not None and type(y.grad_fn).__name__.startswith('_StemConv')
+    w = conv.weight.detach()
+    exact = torch.nn.functional.conv2d(tf32(x).double(), tf32(w).double(), None, 2, 3).float()
+    torch.testing.assert_close(y, exact, rtol=1e-4, atol=1e-4)
+    full = torch.nn.functional.conv2d(x.double(), w.double(), None, 2, 3).float()
+    torch.testing.assert_close(y, full, rtol=5e-3, atol=5e-3)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wd = w.double().requires_grad_(True)
+    torch.nn.functional.conv2d(tf32(x).double(), wd, None, 2, 3).backward(tf32(dy).double())
+    scale = wd.grad.abs().max().item()
+    assert (conv.weight.grad.double() - wd.grad).abs().max().item() < 2e-4 * scale + 1e-4
+
+
 def test_stem_conv_inside_resnet_training_step():
     """the whole bf16 twin path (stem conv + fused BN + max-pool) produces finite,
     decreasing losses -- see test_flagship_gpu for the trainer-level checks."""
