@@ -61,6 +61,8 @@ def parse():
     ap.add_argument('--autocast', action='store_true',
                     help='bf16 via torch.autocast instead of the bf16 shadow-weight twin')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-local', action='store_true',
+                    help='skip the gossip-disabled re-measurement behind `exposed_comm` (N > 1)')
     return ap.parse_args()
 
 
@@ -229,7 +231,31 @@ def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
                'last_loss': round(rows[-1][0], 4), 'last_prec1': round(rows[-1][1], 3),
                'last_prec5': round(rows[-1][2], 3)}
     trainer.finish()
+
+    # ---- exposed communication: the same step with gossip switched off (every rank trains alone,
+    # SGD-only fused kernel), timed the same way on the same GPUs right after -- the difference is
+    # what gossip costs per step after all overlap (kernel time + waiting for the in-neighbours)
+    exposed = None
+    if world > 1 and args.algo != 'ar' and not args.skip_local:
+        model.gossip_enable = False
+        trainer.graph = None
+        trainer._eager_steps = 0
+        for i in range(5):
+            trainer.step(*pool[i % len(pool)])
+        sync_all()
+        e0.record(trainer.stream)
+        for i in range(K):
+            trainer.step_resident()
+        e1.record(trainer.stream)
+        sync_all()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        local_ms = ms3.item() / K
+        exposed = {'ms_per_step': round(ms / K - local_ms, 4), 'local_only_ms_per_step': round(local_ms, 4),
+                   'how': 'same captured step with gossip disabled (SGD-only kernel), same GPUs, max over ranks'}
+        trainer.finish()
     res = {'value': round(value, 2), 'ms_per_step': round(ms / K, 4), 'e2e': e2e, 'clocks': clocks,
+           'exposed_comm': exposed,
            'launches_per_step': launches_per_step, 'graph_name': graph_name,
            'native_ops': native.describe_paths() if hasattr(native, 'describe_paths') else None}
     del trainer, model, net, pool
@@ -310,7 +336,7 @@ def run_ours(args):
                        'loss': 'fused softmax-xent + prec@1/5 kernel inside the captured step',
                        'l2': 'per-step working set (activations+weights > 1 GB) exceeds the '
                              '126 MB L2; no explicit flush'},
-            'clocks': main['clocks'], 'e2e': main['e2e'],
+            'clocks': main['clocks'], 'e2e': main['e2e'], 'exposed_comm': main['exposed_comm'],
             'gpu_launches': (main['launches_per_step'] or 0) * K,
             'gpu_launches_per_step': main['launches_per_step'],
             'secondary': secondary,

@@ -28,6 +28,8 @@ def main():
     ap.add_argument('--bf16', action='store_true')
     ap.add_argument('--segments', type=int, default=4)
     ap.add_argument('--mode', default='mix', choices=['mix', 'mix_nosgd', 'publish', 'gather', 'local'])
+    ap.add_argument('--no-pipe', action='store_true',
+                    help='register-staged sgp_step_kernel instead of the warp-specialised TMA kernel')
     args = ap.parse_args()
 
     multi = 'RANK' in os.environ
@@ -51,6 +53,7 @@ def main():
     eng = GossipEngine(sw, z, graph, sgp.UniformMixing(graph, dev), grad=grad, momentum=mom,
                        shadow=shadow, with_residual=True, grid=args.grid, timeout_s=20.0,
                        segments=args.segments)
+    eng.ctx.set_pipe(not args.no_pipe)
     eng.set_hyper(1e-3, 0.9, 1e-4, True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -102,7 +105,7 @@ def main():
     nvlink_bytes = n_in * n * 4
     if rank == 0:
         print(json.dumps({'mode': args.mode, 'world': world, 'ppi': args.ppi, 'numel': n,
-                          'grid': eng.grid, 'segments': args.segments, 'ms_median': round(med, 4), 'ms_best': round(best, 4),
+                          'grid': eng.grid, 'segments': args.segments, 'pipe': not args.no_pipe, 'ms_median': round(med, 4), 'ms_best': round(best, 4),
                           'nvlink_GBps_per_rank': round(nvlink_bytes / med / 1e6, 1),
                           'bf16': args.bf16}))
     if multi:

@@ -25,7 +25,15 @@ def main():
     ap.add_argument('--iters', type=int, default=6)
     ap.add_argument('--bf16', action='store_true')
     ap.add_argument('--mode', default='mix', choices=['mix', 'local', 'gather'])
+    ap.add_argument('--two-gpu', action='store_true',
+                    help='ONE process, two GPUs (LocalWorld over plain peer access): rank 0 on cuda:0 pulls '
+                         "rank 1's outbox from cuda:1 over NVLink.  The launches are serialised (r1.publish -> "
+                         'r0.mix -> r1.gather) so that the capture works under ncu, which runs one kernel of '
+                         'the process at a time: every flag r0.mix waits for is already set when it starts.')
+    ap.add_argument('--no-pipe', action='store_true')
     args = ap.parse_args()
+    if args.two_gpu:
+        return two_gpu(args)
     dev = torch.device('cuda', 0)
     n = args.numel
     graph = sgp.NPeerDynamicDirectedExponentialGraph(0, 1)
@@ -63,6 +71,47 @@ def main():
         torch.cuda.synchronize()
     eng.check()
     print('ok', eng.device_step)
+
+
+def two_gpu(args):
+    n = args.numel
+    lw = LocalWorld(2, [0, 1])
+    engs = []
+    for r in range(2):
+        dev = torch.device('cuda', r)
+        torch.cuda.set_device(dev)
+        graph = sgp.NPeerDynamicDirectedExponentialGraph(r, 2)
+        z = torch.randn(n, device=dev)
+        grad = torch.randn(n, device=dev)
+        eng = GossipEngine(lw.view(r), z, graph, sgp.UniformMixing(graph, dev), grad=grad,
+                           momentum=torch.zeros(n, device=dev), timeout_s=5.0, with_residual=True, gather_grid=32)
+        eng.ctx.set_pipe(not args.no_pipe)
+        eng.set_hyper(1e-3, 0.9, 1e-4, True)
+        engs.append(eng)
+    flush = [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device('cuda', r)) for r in range(2)]
+    ms = []
+    for it in range(args.iters):
+        for r in range(2):
+            torch.cuda.set_device(r)
+            flush[r].zero_()
+        torch.cuda.set_device(1)
+        engs[1].publish(sgd=False)                      # rank 1's outbox + flags for this step
+        torch.cuda.synchronize(1)
+        torch.cuda.set_device(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engs[0].mix(sgd=True, zero_grad=False)          # the profiled launch: SGD + publish + NVLink pull + mix
+        e1.record()
+        torch.cuda.synchronize(0)
+        ms.append(e0.elapsed_time(e1))
+        torch.cuda.set_device(1)
+        engs[1].gather()                                # rank 1 pulls rank 0's outbox and acks it
+        torch.cuda.synchronize(1)
+    for e in engs:
+        e.check()
+    ms = sorted(ms[2:]) if len(ms) > 2 else ms
+    print('two-gpu mix (flags pre-set, no peer skew): median %.4f ms -> %.1f GB/s pulled over NVLink; steps %d / %d'
+          % (ms[len(ms) // 2], n * 4 / ms[len(ms) // 2] / 1e6, engs[0].device_step, engs[1].device_step))
 
 
 if __name__ == '__main__':

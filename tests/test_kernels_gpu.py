@@ -14,6 +14,15 @@ from stochastic_gradient_push_b200.ops import oracle
 pytestmark = pytest.mark.gpu
 
 CHUNK = 4096
+PIPE = [True]
+
+
+@pytest.fixture(autouse=True, params=[True, False], ids=['pipe', 'regs'])
+def _step_kernel_variant(request):
+    """every test runs with both implementations of the full gossip step: the warp-specialised
+    TMA kernel (sgp_step_pipe_kernel, default) and the register-staged one (sgp_step_kernel)"""
+    PIPE[0] = request.param
+    yield
 
 
 def _mk_world(n, numel, graph_cls, ppi, mixing_cls=None, with_sgd=True, bf16=False,
@@ -37,6 +46,7 @@ def _mk_world(n, numel, graph_cls, ppi, mixing_cls=None, with_sgd=True, bf16=Fal
                          momentum=mom if with_sgd else None, shadow=shadow,
                          with_residual=overlap, grid=grid, gather_grid=4, timeout_s=10.0,
                          name='t')
+        e.ctx.set_pipe(PIPE[0])
         engines.append(e)
         graphs.append(g)
         mixings.append(m)
