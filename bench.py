@@ -60,6 +60,8 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--autocast', action='store_true',
                     help='bf16 via torch.autocast instead of the bf16 shadow-weight twin')
+    ap.add_argument('--adpsgd-rounds', type=int, default=4,
+                    help='AD-PSGD: bilateral rounds a rank may start per applied gradient (0 = unbounded)')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-local', action='store_true',
                     help='skip the gossip-disabled re-measurement behind `exposed_comm` (N > 1)')
@@ -146,6 +148,17 @@ def _build(args, dtype, bs, rank, world, dev):
         trainer = ARTrainer(model, lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True,
                             amp_dtype=amp, use_cuda_graph=not args.no_graph)
         return net, model, trainer, 'all-reduce'
+    if args.algo == 'adpsgd':
+        from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel, make_bilat_trainer
+        model = BilatGossipDataParallel(net, rank=rank, world_size=world,
+                                        graph_class=sgp.DynamicBipartiteExponentialGraph,
+                                        mixing_class=sgp.UniformMixing, lr=lr, momentum=0.9,
+                                        weight_decay=1e-4, nesterov=True, verbose=False,
+                                        heartbeat_timeout=60, max_rounds_per_update=(args.adpsgd_rounds or None))
+        trainer = make_bilat_trainer(model, lr, amp_dtype=amp, use_cuda_graph=not args.no_graph)
+        model.train()
+        model.enable_gossip()
+        return net, model, trainer, 'dynamic bipartite exponential (bilateral)'
     if args.algo == 'dpsgd':
         graph = sgp.RingGraph(rank, world, peers_per_itr=args.ppi)
         graph_name = 'static ring'
@@ -231,15 +244,19 @@ def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
                'last_loss': round(rows[-1][0], 4), 'last_prec1': round(rows[-1][1], 3),
                'last_prec5': round(rows[-1][2], 3)}
     trainer.finish()
+    rounds = int(model.rounds_completed) if args.algo == 'adpsgd' else None
 
     # ---- exposed communication: the same step with gossip switched off (every rank trains alone,
     # SGD-only fused kernel), timed the same way on the same GPUs right after -- the difference is
     # what gossip costs per step after all overlap (kernel time + waiting for the in-neighbours)
     exposed = None
     if world > 1 and args.algo != 'ar' and not args.skip_local:
-        model.gossip_enable = False
-        trainer.graph = None
-        trainer._eager_steps = 0
+        if args.algo == 'adpsgd':
+            model.disable_gossip()           # the captured graph is forward/backward only
+        else:
+            model.gossip_enable = False
+            trainer.graph = None
+            trainer._eager_steps = 0
         for i in range(5):
             trainer.step(*pool[i % len(pool)])
         sync_all()
@@ -254,8 +271,10 @@ def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
         exposed = {'ms_per_step': round(ms / K - local_ms, 4), 'local_only_ms_per_step': round(local_ms, 4),
                    'how': 'same captured step with gossip disabled (SGD-only kernel), same GPUs, max over ranks'}
         trainer.finish()
+    if args.algo == 'adpsgd':
+        model.shutdown()
     res = {'value': round(value, 2), 'ms_per_step': round(ms / K, 4), 'e2e': e2e, 'clocks': clocks,
-           'exposed_comm': exposed,
+           'exposed_comm': exposed, 'gossip_rounds': rounds,
            'launches_per_step': launches_per_step, 'graph_name': graph_name,
            'native_ops': native.describe_paths() if hasattr(native, 'describe_paths') else None}
     del trainer, model, net, pool
@@ -291,14 +310,6 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
 
     bs, K, W = args.batch_size, args.steps, args.warmup
-    if args.algo == 'adpsgd':
-        amp = torch.bfloat16 if args.dtype == 'bf16' else None
-        torch.manual_seed(1 + rank)
-        net = models.MODEL_ZOO[args.model]()
-        models.init_imagenet_in_1hr(net)
-        net = net.to(dev).to(memory_format=torch.channels_last)
-        return run_adpsgd(args, net, rank, world, dev, amp)
-
     main = measure(args, args.dtype, bs, K, W, rank, world, dev, sample_clocks=True)
     # secondary, clearly labelled lines: the other precision at the headline batch, and the
     # reference's per-GPU batch (32 images per GPU in its 8-GPU-per-node job scripts), where the
@@ -337,6 +348,7 @@ def run_ours(args):
                        'l2': 'per-step working set (activations+weights > 1 GB) exceeds the '
                              '126 MB L2; no explicit flush'},
             'clocks': main['clocks'], 'e2e': main['e2e'], 'exposed_comm': main['exposed_comm'],
+            'gossip_rounds_completed_rank0': main['gossip_rounds'],
             'gpu_launches': (main['launches_per_step'] or 0) * K,
             'gpu_launches_per_step': main['launches_per_step'],
             'secondary': secondary,
@@ -344,87 +356,6 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
-
-
-def run_adpsgd(args, net, rank, world, dev, amp):
-    """AD-PSGD (BilatGossipDataParallel): asynchronous by construction, so the step is
-    the reference-style eager loop (forward, backward hook = push grads + pull model,
-    local step); gossip + the gossip-side fused SGD run on the low-priority stream."""
-    import torch
-    import torch.distributed as dist
-    import stochastic_gradient_push_b200 as sgp
-    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel
-    bs, K, W = args.batch_size, args.steps, args.warmup
-    lr = 0.1 * bs * world / 256
-    model = BilatGossipDataParallel(net, rank=rank, world_size=world,
-                                    graph_class=sgp.DynamicBipartiteExponentialGraph,
-                                    mixing_class=sgp.UniformMixing, lr=lr, momentum=0.9,
-                                    weight_decay=1e-4, nesterov=True, verbose=False,
-                                    heartbeat_timeout=60)
-    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True)
-    crit = torch.nn.CrossEntropyLoss()
-    g = torch.Generator().manual_seed(1234 + rank)
-    pool = [(torch.randn(bs, 3, 224, 224, generator=g).pin_memory(),
-             torch.randint(0, 1000, (bs,), generator=g).pin_memory()) for _ in range(4)]
-    loss_host = torch.zeros(K + W + 8).pin_memory()
-    model.train()
-    model.enable_gossip()
-
-    def step(i):
-        x, y = pool[i % 4]
-        x = x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
-        y = y.to(dev, non_blocking=True)
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp is not None):
-            loss = crit(model(x).float(), y)
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=False)
-        loss_host[i:i + 1].copy_(loss.detach().view(1), non_blocking=True)
-
-    for i in range(max(W, 5)):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0))) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rounds0 = model.rounds_completed
-    e0.record()
-    for i in range(K):
-        step(W + i)
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    rounds = torch.tensor([float(model.rounds_completed - rounds0)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rounds, op=dist.ReduceOp.MIN)
-    ms = ms.item()
-    value = bs * world * K / (ms / 1e3)
-    model.disable_gossip()
-    if rank == 0:
-        print(json.dumps({
-            'metric': 'resnet50_adpsgd_images_per_sec', 'value': round(value, 2), 'unit': 'images/s',
-            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': round(ms / K, 4),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
-            'data': 'synthetic', 'impl': 'ours', 'value_is_e2e': True,
-            'config': {'model': args.model, 'algorithm': 'adpsgd', 'graph': 'dynamic bipartite exponential',
-                       'per_gpu_batch': bs, 'global_batch': bs * world, 'image': '3x224x224',
-                       'parallelism': 'dp%d-bilateral-gossip' % world, 'cuda_graph': False,
-                       'gossip_rounds_in_timed_region_min_over_ranks': int(rounds.item()),
-                       'l2': 'per-step working set exceeds the 126 MB L2; no explicit flush'},
-            'clocks': clocks,
-            'e2e': {'value': round(value, 2), 'unit': 'images/s',
-                    'h2d_bytes_per_step': pool[0][0].numel() * 4 + bs * 8, 'd2h_bytes_per_step': 4},
-            'gpu_launches': None}))
-    if world > 1:
-        dist.barrier()
-    model.shutdown()
-    if world > 1:
         dist.destroy_process_group()
 
 

@@ -13,7 +13,11 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -239,6 +243,37 @@ public:
             SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
     }
 
+    // ---- AD-PSGD building blocks (all stream-ordered, no host decisions) ----
+    void bilat_decide(int pub_grid, bool passive, double max_wait_us, c10::optional<torch::Tensor> host_fb)
+    {
+        SgpArgs a = prepare(0);
+        uint32_t* fb = nullptr;
+        if (host_fb.has_value() && host_fb->defined()) {
+            void* dev = nullptr;
+            SGP_CUDA_CHECK(cudaHostGetDevicePointer(&dev, host_fb->data_ptr(), 0));
+            fb = reinterpret_cast<uint32_t*>(dev);
+        }
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_bilat_decide(&a, pub_grid, passive ? 1 : 0,
+                                               (unsigned long long)(max_wait_us * 1e3), fb,
+                                               at::cuda::getCurrentCUDAStream()));
+    }
+    void bilat_work(int grid)
+    {
+        check_grid(grid);
+        SgpArgs a = prepare(SGP_F_FROM_STATE | (args_.shadow ? SGP_F_SHADOW : 0u));
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_step(&a, grid, at::cuda::getCurrentCUDAStream()));
+    }
+    void bilat_ctl(int budget, int enabled)
+    {
+        c10::cuda::CUDAGuard guard(device_);
+        SGP_CUDA_CHECK(sgp_launch_bilat_ctl(args_.st, budget, enabled, at::cuda::getCurrentCUDAStream()));
+    }
+    // raw access for the native gossip daemon
+    SgpArgs raw_args(unsigned int flags) const { return prepare(flags); }
+    int device() const { return device_; }
+
     void set_pipe(bool on) { use_pipe_ = on; }
     bool pipe() const { return use_pipe_; }
 
@@ -319,6 +354,129 @@ private:
     torch::Tensor mom_keep_;
 };
 
+// ---------------------------------------------------------------------------
+// BilatDaemon: the AD-PSGD gossip loop as a NATIVE thread.
+//
+// The reference runs its gossip loop in a separate *process* with its own process group
+// (gossip/ad_psgd.py:253-366).  Here it is a C++ thread inside the training process that never
+// touches the Python interpreter (no GIL): it keeps enqueueing {decide, work} kernel pairs on a
+// dedicated lowest-priority stream, at most `depth` pairs ahead of the GPU (throttled with a ring
+// of events, cudaEventSynchronize -- not a stream synchronize, and never from Python), and backs
+// off while the device-side state machine reports "nothing to do" through a pinned feedback word.
+// The training thread takes the daemon's mutex (lock()/unlock(), exposed to Python as a context
+// manager) to enqueue its own work on the same stream -- gradient application + model pull -- so
+// those are ordered against whole gossip rounds exactly like the reference's gossip_lock.
+// ---------------------------------------------------------------------------
+class BilatDaemon {
+public:
+    BilatDaemon(std::shared_ptr<GossipContext> ctx, int grid, bool passive, double max_wait_us, int depth,
+                double idle_sleep_us)
+        : ctx_(std::move(ctx)), grid_(grid), passive_(passive), max_wait_us_(max_wait_us),
+          depth_(depth < 1 ? 1 : (depth > 8 ? 8 : depth)), idle_sleep_us_(idle_sleep_us)
+    {
+        device_ = ctx_->device();
+        c10::cuda::CUDAGuard guard(device_);
+        int lo = 0, hi = 0;
+        SGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SGP_CUDA_CHECK(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));
+        void* hp = nullptr;
+        SGP_CUDA_CHECK(cudaHostAlloc(&hp, 8 * 4 * sizeof(uint32_t), cudaHostAllocMapped));
+        std::memset(hp, 0, 8 * 4 * sizeof(uint32_t));
+        fb_host_ = reinterpret_cast<volatile uint32_t*>(hp);
+        void* dp = nullptr;
+        SGP_CUDA_CHECK(cudaHostGetDevicePointer(&dp, hp, 0));
+        fb_dev_ = reinterpret_cast<uint32_t*>(dp);
+        for (int i = 0; i < 8; ++i) SGP_CUDA_CHECK(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
+    }
+    ~BilatDaemon() { stop(); }
+
+    void start()
+    {
+        if (running_.exchange(true)) return;
+        stop_ = false;
+        thread_ = std::thread([this] { loop(); });
+    }
+    void stop()
+    {
+        stop_ = true;
+        if (thread_.joinable()) thread_.join();
+        running_ = false;
+    }
+    void lock() { mu_.lock(); }
+    void unlock() { mu_.unlock(); }
+    int64_t stream_handle() const { return reinterpret_cast<int64_t>(stream_); }
+    long long pairs_enqueued() const { return pairs_.load(); }
+    long long rounds_completed() const { return rounds_.load(); }
+    long long idle_polls() const { return idle_.load(); }
+    int last_status() const { return status_.load(); }
+    std::string error() const { std::lock_guard<std::mutex> g(err_mu_); return error_; }
+
+private:
+    void loop()
+    {
+        cudaSetDevice(device_);
+        long long i = 0;
+        bool recorded[8] = {};
+        while (!stop_) {
+            const int slot = (int)(i % depth_);
+            if (recorded[slot]) {
+                // the pair enqueued `depth` iterations ago must have run before its slot is reused
+                cudaError_t e = cudaEventSynchronize(events_[slot]);
+                if (e != cudaSuccess) { fail(std::string("cudaEventSynchronize: ") + cudaGetErrorString(e)); return; }
+                const uint32_t cmd = fb_host_[slot * 4 + 0];
+                rounds_ = (long long)fb_host_[slot * 4 + 1];
+                status_ = (int)fb_host_[slot * 4 + 2];
+                if (cmd == 0u) {
+                    ++idle_;
+                    std::this_thread::sleep_for(std::chrono::microseconds((long long)idle_sleep_us_));
+                }
+            }
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                SgpArgs a = ctx_->raw_args(0);
+                cudaError_t e = sgp_launch_bilat_decide(&a, grid_, passive_ ? 1 : 0,
+                                                        (unsigned long long)(max_wait_us_ * 1e3),
+                                                        fb_dev_ + slot * 4, stream_);
+                if (e == cudaSuccess) {
+                    SgpArgs w = ctx_->raw_args(SGP_F_FROM_STATE | (a.shadow ? SGP_F_SHADOW : 0u));
+                    e = sgp_launch_step(&w, grid_, stream_);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(events_[slot], stream_);
+                if (e != cudaSuccess) { fail(std::string("gossip launch: ") + cudaGetErrorString(e)); return; }
+                g_sgp_kernel_launches += 2;
+            }
+            recorded[slot] = true;
+            ++pairs_;
+            ++i;
+        }
+        cudaStreamSynchronize(stream_);
+    }
+    void fail(const std::string& what)
+    {
+        std::lock_guard<std::mutex> g(err_mu_);
+        error_ = what;
+    }
+
+    std::shared_ptr<GossipContext> ctx_;
+    int grid_;
+    bool passive_;
+    double max_wait_us_;
+    int depth_;
+    double idle_sleep_us_;
+    int device_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t events_[8] = {};
+    volatile uint32_t* fb_host_ = nullptr;
+    uint32_t* fb_dev_ = nullptr;
+    std::thread thread_;
+    std::mutex mu_;
+    mutable std::mutex err_mu_;
+    std::string error_;
+    std::atomic<bool> stop_{false}, running_{false};
+    std::atomic<long long> pairs_{0}, rounds_{0}, idle_{0};
+    std::atomic<int> status_{0};
+};
+
 static void scale_(torch::Tensor x, torch::Tensor scalar, bool invert,
                    c10::optional<torch::Tensor> shadow)
 {
@@ -333,6 +491,88 @@ static void scale_(torch::Tensor x, torch::Tensor scalar, bool invert,
                                     invert ? 1 : 0, sh, at::cuda::getCurrentCUDAStream()));
 }
 
+// dst = scale * sum(srcs): flat fp32 buffers of equal length, possibly on peer GPUs of this process
+static void peer_reduce_(torch::Tensor dst, std::vector<torch::Tensor> srcs, double scale)
+{
+    TORCH_CHECK(dst.is_cuda() && dst.scalar_type() == torch::kFloat32 && dst.is_contiguous());
+    TORCH_CHECK(!srcs.empty() && (int)srcs.size() <= SGP_MAX_RANKS && dst.numel() % 4 == 0);
+    std::vector<const float*> ptrs;
+    for (auto& t : srcs) {
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.is_contiguous() &&
+                    t.numel() == dst.numel());
+        if (t.get_device() != dst.get_device())
+            TORCH_CHECK(enable_peer_access(dst.get_device(), t.get_device()), "no peer access");
+        ptrs.push_back(t.data_ptr<float>());
+    }
+    c10::cuda::CUDAGuard guard(dst.get_device());
+    SGP_CUDA_CHECK(sgp_launch_peer_reduce(dst.data_ptr<float>(), ptrs.data(), (int)ptrs.size(), dst.numel(),
+                                          (float)scale, at::cuda::getCurrentCUDAStream()));
+}
+
+// ---------------------------------------------------------------------------
+// NVLS collectives (csrc/nvls_kernels.cu)
+// ---------------------------------------------------------------------------
+struct NvlsArgs {
+    float* z; float* z_mc; void* g_mc; float* m; SgpSignalPad* const* pads; SgpState* st; const SgpHyper* hyper;
+    long long n; int rank, world; unsigned long long timeout_ns; int grad_bf16; float scale;
+};
+extern "C" {
+cudaError_t sgp_launch_nvls_allreduce(const NvlsArgs* a, int fused_sgd, int grid, cudaStream_t stream);
+cudaError_t sgp_launch_nvls_bcast(float* dst_mc, const float* src, long long n, SgpSignalPad* const* pads,
+                                  SgpState* st, int rank, int world, int root, unsigned long long timeout_ns,
+                                  int grid, cudaStream_t stream);
+int sgp_nvls_max_grid(int device);
+}
+
+// grads (multicast view, fp32 / bf16) -> switch-reduced slice -> [fused SGD-momentum on the slice ->
+// multicast of the new parameters] or [scaled sum multicast back into the gradient buffers]
+static void nvls_allreduce(c10::optional<torch::Tensor> z, c10::optional<torch::Tensor> z_mc, torch::Tensor g_mc,
+                           c10::optional<torch::Tensor> m, torch::Tensor pad_ptrs, torch::Tensor state,
+                           torch::Tensor hyper, int rank, int world, double timeout_s, double scale, bool fused_sgd,
+                           int grid)
+{
+    TORCH_CHECK(g_mc.is_cuda() && (g_mc.scalar_type() == torch::kFloat32 || g_mc.scalar_type() == torch::kBFloat16));
+    TORCH_CHECK(g_mc.numel() % SGP_CHUNK == 0, "buffer length must be a multiple of ", SGP_CHUNK);
+    TORCH_CHECK(pad_ptrs.scalar_type() == torch::kInt64 && pad_ptrs.numel() == world);
+    NvlsArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.g_mc = g_mc.data_ptr();
+    a.grad_bf16 = g_mc.scalar_type() == torch::kBFloat16 ? 1 : 0;
+    a.n = g_mc.numel();
+    if (fused_sgd) {
+        TORCH_CHECK(z.has_value() && z_mc.has_value() && m.has_value(), "fused SGD needs z, z_mc and momentum");
+        TORCH_CHECK(z->numel() == a.n && z_mc->numel() == a.n && m->numel() == a.n);
+        TORCH_CHECK(z->scalar_type() == torch::kFloat32 && m->scalar_type() == torch::kFloat32);
+        a.z = z->data_ptr<float>();
+        a.z_mc = z_mc->data_ptr<float>();
+        a.m = m->data_ptr<float>();
+    } else {
+        TORCH_CHECK(!a.grad_bf16, "the plain NVLS all-reduce is fp32");
+    }
+    a.pads = reinterpret_cast<SgpSignalPad* const*>(pad_ptrs.data_ptr<int64_t>());
+    a.st = reinterpret_cast<SgpState*>(state.data_ptr());
+    a.hyper = reinterpret_cast<const SgpHyper*>(hyper.data_ptr());
+    a.rank = rank;
+    a.world = world;
+    a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    a.scale = (float)scale;
+    c10::cuda::CUDAGuard guard(g_mc.get_device());
+    SGP_CUDA_CHECK(sgp_launch_nvls_allreduce(&a, fused_sgd ? 1 : 0, grid, at::cuda::getCurrentCUDAStream()));
+}
+
+static void nvls_bcast(torch::Tensor dst_mc, torch::Tensor src, torch::Tensor pad_ptrs, torch::Tensor state,
+                       int rank, int world, int root, double timeout_s, int grid)
+{
+    TORCH_CHECK(dst_mc.is_cuda() && dst_mc.scalar_type() == torch::kFloat32 && dst_mc.numel() % 4 == 0);
+    TORCH_CHECK(src.numel() == dst_mc.numel() && src.scalar_type() == torch::kFloat32 && src.is_contiguous());
+    c10::cuda::CUDAGuard guard(dst_mc.get_device());
+    SGP_CUDA_CHECK(sgp_launch_nvls_bcast(dst_mc.data_ptr<float>(), src.data_ptr<float>(), dst_mc.numel(),
+                                         reinterpret_cast<SgpSignalPad* const*>(pad_ptrs.data_ptr<int64_t>()),
+                                         reinterpret_cast<SgpState*>(state.data_ptr()), rank, world, root,
+                                         (unsigned long long)(timeout_s * 1e9), grid,
+                                         at::cuda::getCurrentCUDAStream()));
+}
+
 static void zero_(torch::Tensor x)
 {
     TORCH_CHECK(x.is_cuda() && x.is_contiguous());
@@ -343,10 +583,12 @@ static void zero_(torch::Tensor x)
 }
 
 void bind_bn(py::module& mod);   // bn_bindings.cpp
+void bind_vmm(py::module& mod);  // vmm_symm.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
 {
     bind_bn(mod);
+    bind_vmm(mod);
     mod.doc() = "sm_100a gossip kernels + symmetric-memory runtime";
     mod.def("symm_alloc", &symm_alloc, "allocate IPC-exportable device memory -> (uint8 tensor, handle)");
     mod.def("symm_open", &symm_open, "map a peer's allocation -> uint8 tensor");
@@ -355,6 +597,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
     mod.def("scale_", &scale_, py::arg("x"), py::arg("scalar"), py::arg("invert"),
             py::arg("shadow") = py::none());
     mod.def("zero_", &zero_);
+    mod.def("nvls_allreduce", &nvls_allreduce, py::arg("z"), py::arg("z_mc"), py::arg("g_mc"), py::arg("m"),
+            py::arg("pad_ptrs"), py::arg("state"), py::arg("hyper"), py::arg("rank"), py::arg("world"),
+            py::arg("timeout_s"), py::arg("scale"), py::arg("fused_sgd"), py::arg("grid"));
+    mod.def("nvls_bcast", &nvls_bcast);
+    mod.def("nvls_max_grid", &sgp_nvls_max_grid);
+    mod.def("peer_reduce_", &peer_reduce_, py::arg("dst"), py::arg("srcs"), py::arg("scale") = 1.0);
     mod.def("launch_count", []() { return (long long)g_sgp_kernel_launches.load(); },
             "kernels of this extension launched (or captured) so far by this process");
     mod.def("max_resident_ctas", &sgp_max_resident_ctas);
@@ -387,7 +635,27 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
     mod.attr("F_KEEP_Z") = (unsigned)SGP_F_KEEP_Z;
     mod.attr("F_SELF_FROM_Z") = (unsigned)SGP_F_SELF_FROM_Z;
 
-    py::class_<GossipContext>(mod, "GossipContext")
+    py::class_<BilatDaemon>(mod, "BilatDaemon")
+        .def(py::init<std::shared_ptr<GossipContext>, int, bool, double, int, double>(), py::arg("ctx"),
+             py::arg("grid"), py::arg("passive"), py::arg("max_wait_us") = 50.0, py::arg("depth") = 2,
+             py::arg("idle_sleep_us") = 100.0)
+        .def("start", &BilatDaemon::start)
+        .def("stop", &BilatDaemon::stop, py::call_guard<py::gil_scoped_release>())
+        .def("lock", &BilatDaemon::lock, py::call_guard<py::gil_scoped_release>())
+        .def("unlock", &BilatDaemon::unlock)
+        .def("stream_handle", &BilatDaemon::stream_handle)
+        .def("pairs_enqueued", &BilatDaemon::pairs_enqueued)
+        .def("rounds_completed", &BilatDaemon::rounds_completed)
+        .def("idle_polls", &BilatDaemon::idle_polls)
+        .def("last_status", &BilatDaemon::last_status)
+        .def("error", &BilatDaemon::error);
+
+    mod.attr("STATE_OFF_BILAT_ROUND") = (int)offsetof(SgpState, bilat_round);
+    mod.attr("STATE_OFF_BILAT_BUDGET") = (int)offsetof(SgpState, bilat_budget);
+    mod.attr("STATE_OFF_BILAT_ENABLED") = (int)offsetof(SgpState, bilat_enabled);
+    mod.attr("F_FROM_STATE") = (unsigned)SGP_F_FROM_STATE;
+
+    py::class_<GossipContext, std::shared_ptr<GossipContext>>(mod, "GossipContext")
         .def(py::init<torch::Tensor, c10::optional<torch::Tensor>, c10::optional<torch::Tensor>,
                       c10::optional<torch::Tensor>, c10::optional<torch::Tensor>, torch::Tensor,
                       c10::optional<torch::Tensor>, torch::Tensor, torch::Tensor, int, int,
@@ -402,6 +670,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("set_grad2", &GossipContext::set_grad2)
         .def("set_timeout", &GossipContext::set_timeout)
         .def("set_segments", &GossipContext::set_segments)
+        .def("bilat_decide", &GossipContext::bilat_decide, py::arg("pub_grid"), py::arg("passive"),
+             py::arg("max_wait_us") = 50.0, py::arg("host_fb") = py::none())
+        .def("bilat_work", &GossipContext::bilat_work)
+        .def("bilat_ctl", &GossipContext::bilat_ctl, py::arg("budget") = -1, py::arg("enabled") = -1)
         .def("set_pipe", &GossipContext::set_pipe)
         .def("pipe", &GossipContext::pipe)
         .def("segments", &GossipContext::segments)

@@ -62,7 +62,12 @@ struct __align__(128) SgpState {
     uint32_t bilat_round;   // AD-PSGD rounds completed
     uint32_t bilat_done;    // last probe outcome (1 = partner has published)
     uint32_t ack_from;      // outbox WAR fence only applies to steps >= ack_from + 2
-    uint32_t _pad[21];
+    // AD-PSGD device-side round state machine (sgp_bilat_decide_kernel + SGP_F_FROM_STATE)
+    uint32_t bilat_cmd;        // SGP_F_* bits the next worker launch executes (0 = nothing to do)
+    uint32_t bilat_published;  // 1: this rank's snapshot of the current round is in the outbox
+    uint32_t bilat_budget;     // rounds this rank may still START before its next gradient arrives
+    uint32_t bilat_enabled;    // 0: gossip disabled (an in-flight round still completes)
+    uint32_t _pad[17];
 };
 
 // ---- hyper-parameters (device resident so CUDA graphs can retarget them) ----
@@ -89,6 +94,7 @@ struct SgpHyper {
 #define SGP_F_IN_NUMER   (1u << 9)   // z already holds the numerator x (external optimizer)
 #define SGP_F_KEEP_Z     (1u << 10)  // phase 1 publishes a snapshot but leaves z untouched
 #define SGP_F_SELF_FROM_Z (1u << 11) // phase 2 mixes the CURRENT z (not the published snapshot)
+#define SGP_F_FROM_STATE (1u << 12)  // take the mode bits from SgpState::bilat_cmd (set by the decide kernel)
 
 struct SgpArgs {
     // local buffers (length n, n % SGP_CHUNK == 0)
@@ -241,7 +247,12 @@ cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaS
 cudaError_t sgp_launch_gather_tma(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
 cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_flag,
                              cudaStream_t stream);
+cudaError_t sgp_launch_bilat_decide(const SgpArgs* args, int pub_grid, int passive,
+                                    unsigned long long max_wait_ns, uint32_t* host_fb, cudaStream_t stream);
+cudaError_t sgp_launch_bilat_ctl(SgpState* st, int budget, int enabled, cudaStream_t stream);
 cudaError_t sgp_launch_zero(void* p, long long bytes, cudaStream_t stream);
+cudaError_t sgp_launch_peer_reduce(float* dst, const float* const* srcs, int nsrc, long long n, float scale,
+                                   cudaStream_t stream);
 cudaError_t sgp_launch_scale(float* x, long long n, const float* scalar, int invert,
                              __nv_bfloat16* shadow, cudaStream_t stream);
 cudaError_t sgp_launch_barrier(SgpSignalPad* const* pads, SgpState* st, int rank, int world,

@@ -83,7 +83,13 @@ sgp_step_kernel(const SgpArgs a)
     SgpState* st = a.st;
     const uint32_t step   = *((volatile uint32_t*)&st->step);
     const uint32_t parity = step & 1u;
-    const uint32_t flags  = a.flags;
+    // AD-PSGD: the mode bits come from the device-side round state machine (what the preceding
+    // sgp_bilat_decide_kernel decided); nothing to do -> the whole grid exits at once
+    const bool from_state = (a.flags & SGP_F_FROM_STATE) != 0;
+    const uint32_t flags  = from_state
+        ? ((a.flags & (SGP_F_SHADOW | SGP_F_GRAD_BF16)) | *((volatile uint32_t*)&st->bilat_cmd))
+        : a.flags;
+    if (from_state && (flags & (SGP_F_PHASE1 | SGP_F_PHASE2)) == 0u) return;
     const int      tid    = threadIdx.x;
     const int      b      = blockIdx.x;
     const long long nchunks = a.n / SGP_CHUNK;
@@ -304,6 +310,15 @@ sgp_step_kernel(const SgpArgs a)
         if (flags & SGP_F_FOLD_RES) *((volatile float*)&st->res_weight) = 0.f;
         *((volatile uint32_t*)&st->done_ctas) = 0u;
         if (rotate) *((volatile uint32_t*)&st->step) = step + 1u;
+        if (from_state) {                       // bilateral round bookkeeping
+            if (rotate) {                       // round complete
+                st->bilat_published = 0u;
+                st->bilat_round += 1u;
+            } else if (flags & SGP_F_PUBLISH) {
+                st->bilat_published = 1u;       // snapshot is out; the pull follows in a later launch
+            }
+            st->bilat_cmd = 0u;
+        }
         __threadfence();
     }
 }
@@ -553,7 +568,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __maxnreg__(112)
+// 9 warps x 2 CTAs per SM: the register file is split over 4 sub-partitions (16 K registers
+// each), so 18 warps only fit at <= 102 registers per thread -- __launch_bounds__(288, 2) makes
+// ptxas pick 96.  (At 112 registers ncu showed launch__occupancy_limit_registers = 1 block and
+// the kernel ran one CTA per SM, profiles/step_pipe_2gpu_nvlink_ncu_r2_v1.csv.)
+__global__ void __launch_bounds__(PIPE_THREADS, 2)
 sgp_step_pipe_kernel(const SgpArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -743,12 +762,12 @@ sgp_step_pipe_kernel(const SgpArgs a)
                 for (long long it = it_lo; it < it_hi; ++it) {
                     const long long c = b + it * gridDim.x;
                     const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
-                    float4 own[SGP_UNROLL], acc[SGP_UNROLL];
+                    float4 acc[SGP_UNROLL];
 #pragma unroll
                     for (int u = 0; u < SGP_UNROLL; ++u) {
                         const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                        own[u] = ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first);   // L2 hit
-                        acc[u] = mul4(own[u], row.self_w);
+                        acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first),   // L2 hit
+                                      row.self_w);
                     }
                     for (int k = 0; k < n_in; ++k) {
                         mbar_wait(&full[cstage], cphase);
@@ -760,11 +779,13 @@ sgp_step_pipe_kernel(const SgpArgs a)
                         if (lane == 0) mbar_arrive(&empty[cstage]);     // this warp is done with the stage
                         if (++cstage == PIPE_STAGES) { cstage = 0; cphase ^= 1u; }
                     }
-                    const bool failed = s_fail != 0;
+                    const bool failed = s_fail != 0;           // (rare: re-read the own numerator)
 #pragma unroll
                     for (int u = 0; u < SGP_UNROLL; ++u) {
                         const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
-                        const float4 zv = failed ? mul4(own[u], inv_w1) : mul4(acc[u], inv_wn);
+                        const float4 zv = failed
+                            ? mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first), inv_w1)
+                            : mul4(acc[u], inv_wn);
                         st_f4(reinterpret_cast<float4*>(a.z + i), zv);
                         if (flags & SGP_F_SHADOW)
                             st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
@@ -829,6 +850,98 @@ __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* 
         }
         __threadfence_system();
     }
+}
+
+// ---------------------------------------------------------------------------
+// AD-PSGD round state machine, device side.  One CTA decides what the NEXT worker launch
+// (sgp_step_kernel with SGP_F_FROM_STATE) does, from flags only:
+//   * active ranks publish their snapshot unconditionally, passive ranks only once their
+//     partner's snapshot of this round is visible (gossip/gossiper.py:290-316);
+//   * nobody publishes before the readers of round r-2 released the outbox half;
+//   * the pull (x <- 1/2 (x_now + x_partner), ack, advance) runs once both snapshots are out;
+//   * waiting for the partner is BOUNDED (max_wait_ns, ~50 us): if it does not show up the
+//     launch pair does nothing (or only publishes) and the daemon simply enqueues the next
+//     pair -- no kernel ever spins for long, no host synchronisation per poll;
+//   * a rank only STARTS a round while it has budget (rounds per applied gradient) and gossip
+//     is enabled; a round whose snapshot is already out is always completed.
+// host_fb (pinned, optional): [0] = decided bits, [1] = rounds completed, [2] = status word.
+// ---------------------------------------------------------------------------
+__global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, const int passive,
+                                        const unsigned long long max_wait_ns, uint32_t* host_fb)
+{
+    __shared__ int s_all;
+    SgpState* st = a.st;
+    const uint32_t step = *((volatile uint32_t*)&st->step);
+    RowInfo row;
+    load_row(a, step, row);
+    int segs = a.segments < 1 ? 1 : a.segments;
+    if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
+    const uint32_t want = step * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs;
+    const uint32_t published = *((volatile uint32_t*)&st->bilat_published);
+    const bool may_start = (*((volatile uint32_t*)&st->bilat_enabled) != 0u) &&
+                           (*((volatile uint32_t*)&st->bilat_budget) != 0u);
+    const bool engaged = published != 0u || may_start;
+
+    int ready = 0;
+    if (engaged) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (true) {
+            if (threadIdx.x == 0) s_all = 1;
+            __syncthreads();
+            for (int k = 0; k < row.n_in; ++k) {
+                const int j = row.in[k];
+                if (j < 0) continue;
+                for (int f = threadIdx.x; f < pub_grid; f += blockDim.x)
+                    if ((int32_t)(ld_acquire_sys(&a.pads[j]->pub_seq[f]) - want) < 0) s_all = 0;
+            }
+            __syncthreads();
+            ready = s_all;
+            __syncthreads();
+            if (ready || globaltimer_ns() - t0 > max_wait_ns) break;
+            __nanosleep(500);
+        }
+    }
+    if (threadIdx.x != 0) return;
+    uint32_t acks_ok = 1u;
+    if (step >= st->ack_from + 2u) {
+        RowInfo prev;
+        load_row(a, step - 2u, prev);
+        for (int k = 0; k < prev.n_out; ++k) {
+            const int o = prev.out[k];
+            if (o < 0 || o == a.rank) continue;
+            if ((int32_t)(ld_acquire_sys(&a.pads[a.rank]->ack_seq[o]) - (step - 1u)) < 0) acks_ok = 0u;
+        }
+    }
+    const bool do_publish = !published && may_start && acks_ok && (ready || !passive);
+    const bool do_pull = ready && (published || do_publish);
+    uint32_t cmd = 0u;
+    if (do_publish && do_pull)
+        cmd = SGP_F_PHASE1 | SGP_F_PUBLISH | SGP_F_KEEP_Z | SGP_F_PHASE2 | SGP_F_SELF_FROM_Z;
+    else if (do_publish)
+        cmd = SGP_F_PHASE1 | SGP_F_PUBLISH | SGP_F_KEEP_Z | SGP_F_NO_ROTATE;
+    else if (do_pull)
+        cmd = SGP_F_PHASE2 | SGP_F_PUBLISH | SGP_F_SELF_FROM_Z;
+    if (do_publish) {                          // starting a round consumes budget
+        const uint32_t bud = *((volatile uint32_t*)&st->bilat_budget);
+        if (bud != 0xFFFFFFFFu && bud > 0u) st->bilat_budget = bud - 1u;
+    }
+    st->bilat_cmd = cmd;
+    st->bilat_done = (uint32_t)ready;
+    __threadfence();
+    if (host_fb) {
+        ((volatile uint32_t*)host_fb)[0] = cmd;
+        ((volatile uint32_t*)host_fb)[1] = st->bilat_round + (do_pull ? 1u : 0u);
+        ((volatile uint32_t*)host_fb)[2] = st->status;
+        __threadfence_system();
+    }
+}
+
+// budget < 0 / enabled < 0: leave the field alone.  budget == INT_MAX: unbounded
+__global__ void sgp_bilat_ctl_kernel(SgpState* st, int budget, int enabled)
+{
+    if (budget >= 0) st->bilat_budget = (budget == 0x7FFFFFFF) ? 0xFFFFFFFFu : (uint32_t)budget;
+    if (enabled >= 0) st->bilat_enabled = (uint32_t)enabled;
+    __threadfence();
 }
 
 // ---------------------------------------------------------------------------
@@ -969,6 +1082,27 @@ sgp_scale_kernel(float* x, long long n, const float* scalar, int invert, __nv_bf
 }
 
 // ---------------------------------------------------------------------------
+// dst = scale * sum_k srcs[k]   over flat fp32 buffers that may live on PEER devices of the same
+// process (single-process multi-GPU replicas): the reference's reduce_add_coalesced
+// (gossip/distributed.py:523-549, N10) as one kernel of 16-byte P2P loads on the master GPU.
+// ---------------------------------------------------------------------------
+struct SgpPtrList { const float* p[SGP_MAX_RANKS]; int n; };
+
+__global__ void __launch_bounds__(SGP_THREADS)
+sgp_peer_reduce_kernel(float* __restrict__ dst, const SgpPtrList srcs, long long n4, float scale)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < srcs.n; ++k) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(srcs.p[k]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(dst)[i] = mul4(acc, scale);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 extern "C" {
@@ -988,6 +1122,11 @@ cudaError_t sgp_launch_step_pipe(const SgpArgs* args, int grid, cudaStream_t str
         cudaError_t e = cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PIPE_SMEM);
         if (e != cudaSuccess) return e;
+        // two CTAs x 64 KB per SM: ask for the large shared-memory carve-out (the default one fits
+        // a single CTA: launch__occupancy_limit_shared_mem = 1 in the first ncu capture)
+        e = cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     sgp_step_pipe_kernel<<<grid, PIPE_THREADS, PIPE_SMEM, stream>>>(*args);
@@ -1000,6 +1139,8 @@ int sgp_max_resident_ctas_pipe(int device)
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    cudaFuncSetAttribute(sgp_step_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgp_step_pipe_kernel, PIPE_THREADS, PIPE_SMEM)
         != cudaSuccess) return 0;
     return sms * per_sm;
@@ -1032,10 +1173,38 @@ cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_f
     return cudaGetLastError();
 }
 
+cudaError_t sgp_launch_bilat_decide(const SgpArgs* args, int pub_grid, int passive,
+                                    unsigned long long max_wait_ns, uint32_t* host_fb, cudaStream_t stream)
+{
+    sgp_bilat_decide_kernel<<<1, SGP_THREADS, 0, stream>>>(*args, pub_grid, passive, max_wait_ns, host_fb);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_bilat_ctl(SgpState* st, int budget, int enabled, cudaStream_t stream)
+{
+    sgp_bilat_ctl_kernel<<<1, 1, 0, stream>>>(st, budget, enabled);
+    return cudaGetLastError();
+}
+
 cudaError_t sgp_launch_allreduce_sgd(const SgpArgs* args, void* const* grad_peers, int grid,
                                      cudaStream_t stream)
 {
     sgp_allreduce_sgd_kernel<<<grid, SGP_THREADS, 0, stream>>>(*args, grad_peers);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_peer_reduce(float* dst, const float* const* srcs, int nsrc, long long n, float scale,
+                                   cudaStream_t stream)
+{
+    if (nsrc < 1 || nsrc > SGP_MAX_RANKS || (n & 3)) return cudaErrorInvalidValue;
+    SgpPtrList l;
+    l.n = nsrc;
+    for (int k = 0; k < nsrc; ++k) l.p[k] = srcs[k];
+    const long long n4 = n / 4;
+    int grid = (int)((n4 + SGP_THREADS - 1) / SGP_THREADS);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    sgp_peer_reduce_kernel<<<grid, SGP_THREADS, 0, stream>>>(dst, l, n4, scale);
     return cudaGetLastError();
 }
 

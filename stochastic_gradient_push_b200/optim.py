@@ -44,7 +44,11 @@ class FusedGossipSGD(object):
         self._arenas = model._arenas
         self.grad_flat, self.momentum_flat = {}, {}
         for dtype, arena in self._arenas.items():
-            self.grad_flat[dtype] = arena.new_buffer()
+            hier = getattr(model, '_hier_grad', None)
+            # hierarchical mode on the kernel plane: keep accumulating into the symmetric
+            # (multicast-bound) flat gradient so the local-node average stays one NVLS kernel
+            self.grad_flat[dtype] = hier if (hier is not None and dtype == torch.float32) \
+                else arena.new_buffer()
             self.momentum_flat[dtype] = arena.new_buffer(dtype=torch.float32
                                                          if dtype != torch.float64 else dtype)
             arena.bind_grads(model._params_by_dtype[dtype], self.grad_flat[dtype])

@@ -16,13 +16,21 @@ that needs a process:
   with one flat D2D copy, the model is pulled back with one flat D2D copy;
 * the gossip-side optimizer is the fused SGD kernel (``engine.local``);
 * the bilateral average is the pull kernel over NVSwitch peer memory, gated by
-  a device-side flag handshake: ``publish_only`` (snapshot + release flags),
-  ``probe`` (has my partner published this round?  -- the reference's
-  ``_pending_req.is_completed()``), ``pull_only`` (x <- (x + x_partner)/2, ack).
-  Active ranks publish unconditionally, passive ranks only once their partner's
-  snapshot is visible (``gossip/gossiper.py:290-316``); no kernel ever spins;
-* a daemon *thread* drives that loop on a dedicated low-priority stream with a
-  small grid, so training kernels keep the SMs.
+  a DEVICE-SIDE round state machine: ``sgp_bilat_decide_kernel`` (one CTA) reads
+  the partner's publish flags / our ack flags with a bounded (~50 us) wait and
+  writes what the following worker launch does -- publish the snapshot, pull
+  ``x <- (x + x_partner)/2`` + ack + advance, both, or nothing.  Active ranks
+  publish unconditionally, passive ranks only once their partner's snapshot is
+  visible (``gossip/gossiper.py:290-316``); no kernel ever spins for long and the
+  host never decides a transition;
+* the loop that keeps enqueueing {decide, work} pairs is a NATIVE thread
+  (``_C.BilatDaemon``, csrc/bindings.cpp): no GIL, no ``stream.synchronize()`` per
+  poll -- it throttles itself with a ring of CUDA events and a pinned feedback
+  word, on a dedicated lowest-priority stream with a small grid, so training
+  kernels keep the SMs;
+* the training thread takes the daemon's mutex to enqueue {pull the model, apply
+  the new gradients with the fused SGD kernel} on the same stream, which orders
+  them against whole gossip rounds exactly like the reference's ``gossip_lock``.
 
 On CPU tensors / gloo the same loop runs over ``BilatPushPull`` (isend/irecv on
 a dedicated process group) with plain torch SGD -- the oracle for the kernels.
@@ -54,7 +62,8 @@ class BilatGossipDataParallel(Module):
                  weight_decay=1e-4, nesterov=True, verbose=True,
                  network_interface_type=None, tcp_interface_name=None,
                  transport='auto', poll_interval=2e-4, gossip_grid=32,
-                 heartbeat_timeout=300.0, max_rounds_per_update=4):
+                 heartbeat_timeout=300.0, max_rounds_per_update=4, daemon_depth=2,
+                 partner_wait_us=50.0, symmetric_world=None):
         super(BilatGossipDataParallel, self).__init__()
         first = next(module.parameters())
         on_cuda = first.is_cuda
@@ -69,7 +78,8 @@ class BilatGossipDataParallel(Module):
 
         # control plane: reuse the caller's process group, or create the one the
         # reference's gossip process would have created (ad_psgd.py:280-284)
-        if not dist.is_initialized() and world_size is not None and world_size > 1:
+        if not dist.is_initialized() and world_size is not None and world_size > 1 \
+                and symmetric_world is None:
             import os
             if master_addr is not None:
                 os.environ['MASTER_ADDR'] = str(master_addr)
@@ -139,7 +149,7 @@ class BilatGossipDataParallel(Module):
         self.gossip_update_flag = threading.Event()  # learning rate changed
         self._stop = threading.Event()
         self._lr = float(lr)
-        self.rounds_completed = 0
+        self._rounds_completed = 0
         self.grads_applied = 0
         self._error = None
 
@@ -159,16 +169,33 @@ class BilatGossipDataParallel(Module):
         if use_kernels:
             from ..ops.peer_mix import GossipEngine
             from .symmetric import LocalWorld, SymmetricWorld
-            sw = SymmetricWorld(first.device) if world_size > 1 \
-                else LocalWorld(1, [first.device.index]).view(0)
+            if symmetric_world is not None:
+                sw = symmetric_world            # e.g. a LocalWorld view: several ranks in one process
+            else:
+                sw = SymmetricWorld(first.device) if world_size > 1 \
+                    else LocalWorld(1, [first.device.index]).view(0)
             self.engine = GossipEngine(sw, self.gossip_flat, self.graph, self.mixing,
                                        grad=self.gossip_grad_flat, momentum=self.momentum_flat,
                                        grid=gossip_grid, timeout_s=self._timeout_s, name='adpsgd')
-            lo, hi = torch.cuda.Stream.priority_range()
-            self.gossip_stream = torch.cuda.Stream(device=first.device, priority=lo)
-            self._host_flag = self.engine.C.pinned_flag()
             self.engine.set_hyper(lr, momentum, weight_decay, nesterov)
+            self._hyper = (float(lr), momentum, weight_decay, nesterov)
+            # gossip starts disabled (the reference's thread waits for enable_gossip()); a rank
+            # may start `max_rounds_per_update` rounds per applied gradient
+            self._budget = 0x7FFFFFFF if max_rounds_per_update is None else int(max_rounds_per_update)
+            self.engine.ctx.bilat_ctl(self._budget, 0)
             torch.cuda.synchronize(first.device)
+            C = self.engine.C
+            self.daemon = C.BilatDaemon(self.engine.ctx, self.engine.grid, bool(self.graph.is_passive()),
+                                        float(partner_wait_us), int(daemon_depth),
+                                        max(20.0, float(poll_interval) * 1e6))
+            # the daemon owns the (lowest-priority) gossip stream; torch sees it as an external stream
+            self.gossip_stream = torch.cuda.ExternalStream(self.daemon.stream_handle(), device=first.device)
+            self._apply_grid = int(min(self.engine.max_grid, C.MAX_CTAS, self.gossip_flat.numel() // C.CHUNK))
+            self._grads_pending = False
+            self._ev_main = torch.cuda.Event()
+            self._ev_pulled = torch.cuda.Event()
+            if world_size > 1:
+                self.daemon.start()
         else:
             self.gossip_stream = None
             group = None
@@ -183,9 +210,12 @@ class BilatGossipDataParallel(Module):
         self.model_meter = Meter(ptag='Model', stateful=True, csv_format=False)
         self.gossip_meter = Meter(ptag='Gossip', stateful=True, csv_format=False)
         self.gossip_read_flag.set()
-        self.gossip_thread = threading.Thread(target=self._gossip_target, daemon=True,
-                                              name='Gossip-Thread')
-        self.gossip_thread.start()
+        self.gossip_thread = None
+        if self.engine is None:
+            # portable data plane: the loop is a Python thread over isend / irecv
+            self.gossip_thread = threading.Thread(target=self._gossip_target, daemon=True,
+                                                  name='Gossip-Thread')
+            self.gossip_thread.start()
         self.__register_hooks()
 
     # ------------------------------------------------------------------ #
@@ -216,10 +246,16 @@ class BilatGossipDataParallel(Module):
     def enable_gossip(self):
         self.gossip_enable = True
         self.gossip_enable_flag.set()
+        if self.engine is not None:
+            with self._locked_gossip_stream():
+                self.engine.ctx.bilat_ctl(self._budget, 1)
 
     def disable_gossip(self):
         self.gossip_enable = False
         self.gossip_enable_flag.clear()
+        if self.engine is not None:
+            with self._locked_gossip_stream():
+                self.engine.ctx.bilat_ctl(-1, 0)       # a round whose snapshot is out still completes
 
     def block(self):
         return          # the reference's barrier is unreachable too (ad_psgd.py:212-215)
@@ -236,7 +272,67 @@ class BilatGossipDataParallel(Module):
     def shutdown(self):
         self._stop.set()
         self.gossip_enable_flag.set()
-        self.gossip_thread.join(timeout=10)
+        if self.gossip_thread is not None:
+            self.gossip_thread.join(timeout=10)
+        if self.engine is not None:
+            self.daemon.stop()
+
+    @property
+    def rounds_completed(self):
+        """bilateral averaging rounds this rank has completed"""
+        if self.engine is not None:
+            return int(self.daemon.rounds_completed())
+        return self._rounds_completed
+
+    @rounds_completed.setter
+    def rounds_completed(self, v):
+        self._rounds_completed = v
+
+    # ------------------------------------------------------------------ #
+    # kernel data plane: everything the training thread does to the gossip copy is enqueued on
+    # the daemon's stream while holding the daemon's mutex (== the reference's gossip_lock)
+    # ------------------------------------------------------------------ #
+    def _locked_gossip_stream(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.daemon.lock()                     # (blocks without the GIL)
+            try:
+                with torch.cuda.stream(self.gossip_stream):
+                    yield
+            finally:
+                self.daemon.unlock()
+        return cm()
+
+    def _apply_on_gossip_stream(self, grad_is_train_buffer=False):
+        """fused SGD-momentum step of the gossip copy with the pending gradients (+ budget refill)"""
+        e = self.engine
+        lr = self._lr
+        if self._hyper[0] != lr:
+            self._hyper = (lr,) + self._hyper[1:]
+        e.set_hyper(*self._hyper)
+        C = e.C
+        e.ctx.step(C.F_PHASE1 | C.F_NO_ROTATE | C.F_SGD | C.F_ZERO_GRAD, self._apply_grid)
+        e.ctx.bilat_ctl(self._budget, -1)
+        self.grads_applied += 1
+
+    def handoff(self):
+        """Fast path of one training iteration (what the backward hook + ``optimizer.step()`` of
+        the reference loop amount to): apply this step's gradients to the gossip copy with the
+        fused SGD kernel, then pull the result into the training copy -- one enqueue under the
+        daemon lock, the training stream waits only for those two local kernels."""
+        self._check()
+        dev = self.arena.flat.device
+        main = torch.cuda.current_stream(dev)
+        self.gossip_grad_flat.copy_(self.grad_flat, non_blocking=True)
+        self._ev_main.record(main)
+        with self._locked_gossip_stream():
+            self.gossip_stream.wait_event(self._ev_main)
+            self._apply_on_gossip_stream()
+            self.arena.flat.copy_(self.gossip_flat, non_blocking=True)
+            self._ev_pulled.record(self.gossip_stream)
+        main.wait_event(self._ev_pulled)
 
     # ------------------------------------------------------------------ #
     # train-thread <-> gossip-thread hand-offs
@@ -244,23 +340,40 @@ class BilatGossipDataParallel(Module):
     def _check(self):
         if self._error is not None:
             raise RuntimeError('gossip thread died: %r' % (self._error,))
+        if self.engine is not None:
+            err = self.daemon.error()
+            if err:
+                raise RuntimeError('gossip daemon died: %s' % err)
+            if self.daemon.last_status() != 0:
+                raise NameError('Gossip flag timeout (device status %d)' % self.daemon.last_status())
 
     def _pull_model(self):
         """train copy <- gossip copy (one flat copy under the gossip lock)."""
         self._check()
+        if self.engine is not None:
+            # pull first, then apply the gradients handed over by _transfer_grads(): the caller's
+            # own optimizer.step() applies them to the training copy (reference loop order,
+            # gossip_sgd_adpsgd.py:366-370); the training stream waits for the pull only
+            dev = self.arena.flat.device
+            main = torch.cuda.current_stream(dev)
+            self._ev_main.record(main)
+            with self._locked_gossip_stream():
+                self.gossip_stream.wait_event(self._ev_main)
+                self.arena.flat.copy_(self.gossip_flat, non_blocking=True)
+                self._ev_pulled.record(self.gossip_stream)
+                if self._grads_pending:
+                    self._apply_on_gossip_stream()
+                    self._grads_pending = False
+            main.wait_event(self._ev_pulled)
+            return True
         with self.gossip_lock:
-            if self.engine is not None:
-                cur = torch.cuda.current_stream(self.arena.flat.device)
-                cur.wait_stream(self.gossip_stream)
             self.arena.flat.copy_(self.gossip_flat, non_blocking=False)
-            if self.engine is not None:
-                torch.cuda.current_stream(self.arena.flat.device).synchronize()
         return True
 
     def _transfer_grads(self):
         """gossip-side gradient buffer <- this step's gradients."""
         self._check()
-        if not self.gossip_read_flag.wait(timeout=self._timeout_s):
+        if self.engine is None and not self.gossip_read_flag.wait(timeout=self._timeout_s):
             raise RuntimeError('gossip thread did not consume the previous gradients')
         params = list(self.module.parameters())
         g0 = params[0].grad
@@ -275,7 +388,8 @@ class BilatGossipDataParallel(Module):
                 else:
                     g.zero_()
         if self.engine is not None:
-            torch.cuda.current_stream(self.arena.flat.device).synchronize()
+            self._grads_pending = True      # applied (stream-ordered) by the next _pull_model()
+            return True
         self.gossip_read_flag.clear()
         self.train_write_flag.set()
         return True
@@ -285,13 +399,8 @@ class BilatGossipDataParallel(Module):
     # ------------------------------------------------------------------ #
     def _gossip_target(self):
         try:
-            if self.engine is not None:
-                torch.cuda.set_device(self.arena.flat.device)
-                with torch.cuda.stream(self.gossip_stream):
-                    self._loop_kernels()
-            else:
-                with torch.no_grad():
-                    self._loop_c10d()
+            with torch.no_grad():
+                self._loop_c10d()
         except Exception as e:           # surfaced to the train thread
             self._error = e
             self.gossip_read_flag.set()
@@ -300,22 +409,15 @@ class BilatGossipDataParallel(Module):
         """learning-rate updates and fresh gradients -> gossip-side SGD step"""
         if self.gossip_update_flag.is_set():
             cfg['lr'] = self._lr
-            if self.engine is not None:
-                self.engine.set_hyper(cfg['lr'], cfg['momentum'], cfg['weight_decay'],
-                                      cfg['nesterov'])
             self.gossip_update_flag.clear()
         if self.train_write_flag.is_set():
             bt = time.time()
             with self.gossip_lock:
-                if self.engine is not None:
-                    self.engine.local(sgd=True, zero_grad=False)
-                    self.gossip_stream.synchronize()
-                else:
-                    x, m = oracle.sgd_momentum(self.gossip_flat, self.gossip_grad_flat,
-                                               self.momentum_flat, cfg['lr'], cfg['momentum'],
-                                               cfg['weight_decay'], cfg['nesterov'])
-                    self.gossip_flat.copy_(x)
-                    self.momentum_flat.copy_(m)
+                x, m = oracle.sgd_momentum(self.gossip_flat, self.gossip_grad_flat,
+                                           self.momentum_flat, cfg['lr'], cfg['momentum'],
+                                           cfg['weight_decay'], cfg['nesterov'])
+                self.gossip_flat.copy_(x)
+                self.momentum_flat.copy_(m)
             self.grads_applied += 1
             self._rounds_since_update = 0
             self.train_write_flag.clear()
@@ -328,42 +430,6 @@ class BilatGossipDataParallel(Module):
         k = self.max_rounds_per_update
         return (k is not None) and (not round_in_flight) and (self._rounds_since_update >= k) \
             and self.training
-
-    def _loop_kernels(self):
-        cfg = dict(self.dist_config)
-        e = self.engine
-        passive = self.graph.is_passive()
-        alone = self.dist_config['world_size'] < 2
-        published = False
-        while not self._stop.is_set():
-            if not self.gossip_enable_flag.wait(timeout=0.05):
-                continue
-            self._apply_pending(cfg)
-            if alone or self._throttled(published):
-                time.sleep(self._poll)
-                continue
-            bt = time.time()
-            e.probe(self._host_flag)
-            self.gossip_stream.synchronize()
-            ready = int(self._host_flag[0]) == 1        # partner's snapshot is visible
-            may_publish = int(self._host_flag[1]) == 1  # our outbox buffer has been released
-            # active ranks publish unconditionally, passive ranks only once their
-            # partner showed up; never before the readers of round r-2 have acked
-            if not published and may_publish and (ready or not passive):
-                with self.gossip_lock:
-                    e.publish_only()
-                published = True
-            if ready and published:
-                with self.gossip_lock:
-                    e.pull_only()
-                    self.gossip_stream.synchronize()
-                e.check()
-                published = False
-                self.rounds_completed += 1
-                self._rounds_since_update += 1
-                self.gossip_meter.update(time.time() - bt)
-            else:
-                time.sleep(self._poll)
 
     def _loop_c10d(self):
         """Same protocol over isend/irecv.  "Has my partner published?" is a key in
@@ -452,3 +518,99 @@ class BilatGossipDataParallel(Module):
         def queue_hook(*unused):
             Variable._execution_engine.queue_callback(hook)
         return queue_hook
+
+
+# --------------------------------------------------------------------------- #
+# graph-captured AD-PSGD training step
+# --------------------------------------------------------------------------- #
+class _BilatEngineShim(object):
+    """The slice of GossipEngine that GossipTrainer touches, for the bilateral model."""
+
+    def __init__(self, model: BilatGossipDataParallel):
+        self.model = model
+        self.device = model.arena.flat.device
+        self.C = model.engine.C
+        self.steps = 0
+
+    def set_hyper(self, lr, momentum, weight_decay, nesterov, do_sgd=True, grad_scale=1.0):
+        self.model.update_lr(lr)
+
+    def check(self):
+        self.model._check()
+
+
+def make_bilat_trainer(model: BilatGossipDataParallel, lr, criterion=None, amp_dtype=None,
+                       use_cuda_graph=True, warmup_iters=3, channels_last=True):
+    """AD-PSGD counterpart of :class:`~.trainer.GossipTrainer`: forward + fused loss/accuracy +
+    backward are captured ONCE as a CUDA graph; after every replay the gradients are handed to
+    the gossip side with :meth:`BilatGossipDataParallel.handoff` (fused SGD on the gossip copy +
+    model pull, enqueued on the daemon's stream under its lock).  The bilateral averaging itself
+    runs asynchronously on the native daemon's low-priority stream the whole time."""
+    from .trainer import GossipTrainer
+
+    class BilatTrainer(GossipTrainer):
+
+        def __init__(self):
+            assert model.engine is not None, 'BilatTrainer drives the nvlink kernel transport'
+            self.model = model
+
+            class _Opt(object):
+                param_groups = [dict(lr=lr, momentum=model.dist_config['momentum'],
+                                     weight_decay=model.dist_config['weight_decay'],
+                                     nesterov=model.dist_config['nesterov'])]
+                grad_scale = 1.0
+            self.opt = _Opt()
+            self.engine = _BilatEngineShim(model)
+            self.k = None
+            from ..ops.fused_loss import FusedCrossEntropyWithAccuracy
+            self.criterion = criterion or FusedCrossEntropyWithAccuracy()
+            self._fused_loss = isinstance(self.criterion, FusedCrossEntropyWithAccuracy)
+            self.amp_dtype = amp_dtype
+            self.use_graph = use_cuda_graph
+            self.warmup_iters = warmup_iters
+            self.channels_last = channels_last
+            self.device = self.engine.device
+            self.overlap = False
+            self.gossip = False
+            self.graph = None
+            self.static_in = self.static_tgt = self.static_loss = self.static_out = None
+            self.static_metrics = None
+            self._eager_steps = 0
+            import os
+            self.batched_grad_copy = os.environ.get('SGP_B200_BATCHED_GRAD_COPY', '1') != '0'
+            self._grad_slots = None
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = self._stage_tgt = None
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._prefetched = False
+            self._loss_ring = None
+            self._loss_slot = 0
+            self._skip_next_sgd = False
+            self.own_launches_per_step = None
+
+        def _one_step(self, first=False):
+            self._fwd_bwd()                      # the captured part
+
+        def _run_on_stream(self):
+            c0 = self.engine.C.launch_count()
+            super(BilatTrainer, self)._run_on_stream()
+            self.model.handoff()                 # eager: apply gradients + pull, under the daemon lock
+            if self.graph is None or self.own_launches_per_step is None:
+                self.own_launches_per_step = self.engine.C.launch_count() - c0
+            else:
+                self.own_launches_per_step = max(self.own_launches_per_step, 0)
+
+        def _after_replay(self):
+            pass
+
+        def finish(self):
+            torch.cuda.synchronize(self.device)
+            self.model._check()
+
+        def check(self):
+            self.model._check()
+
+    return BilatTrainer()

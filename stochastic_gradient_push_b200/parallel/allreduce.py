@@ -12,6 +12,13 @@ path so the comparison isolates the algorithm:
   with 16-byte P2P loads, sums them in rank order (replicas stay bit-identical),
   scales by 1/world and applies SGD-momentum in the same pass -- one kernel,
   no NCCL call, no bucket copies;
+* ``transport='nvls'`` (the default whenever the GPUs support NVSwitch multicast):
+  ``sgp_nvls_allreduce_kernel`` -- parameters and gradients live in VMM symmetric
+  memory with a multicast mapping; every rank reduces ITS 1/world slice of the
+  gradients inside the switch (``multimem.ld_reduce``), applies SGD-momentum to
+  that slice only (sharded optimizer step) and multicasts the new parameters to
+  every replica (``multimem.st``): ~2 x 4n bytes over NVLink per GPU instead of
+  (world-1) x 4n, bit-identical replicas, still one kernel and no NCCL call;
 * ``transport='nccl'`` keeps a library path (one in-place ``all_reduce`` on the
   flat gradient + the fused local SGD kernel) as a second comparator.
 """
@@ -31,7 +38,7 @@ from .trainer import GossipTrainer
 
 class AllReduceDataParallel(Module):
 
-    def __init__(self, module, rank=None, world_size=None, transport='p2p',
+    def __init__(self, module, rank=None, world_size=None, transport='auto',
                  grad_dtype=torch.float32, timeout_s=60.0, grid=None):
         super().__init__()
         self.module = module
@@ -41,11 +48,28 @@ class AllReduceDataParallel(Module):
             else:
                 rank, world_size = 0, 1
         self.rank, self.world_size = rank, world_size
-        self.transport = transport
         params = list(module.parameters())
         assert all(p.dtype == torch.float32 and p.is_cuda for p in params)
         self.device = params[0].device
-        self.arena = FlatArena(params, device=self.device)
+        from .symmetric import LocalWorld, SymmetricWorld, VmmSymmetricWorld
+        if transport == 'auto':
+            transport = 'nvls' if (world_size > 1 and VmmSymmetricWorld.supported(self.device)) else 'p2p'
+        if transport == 'nvls' and world_size == 1:
+            transport = 'p2p'
+        self.transport = transport
+        self._timeout_s = float(timeout_s)
+        self._z_buf = None
+        if transport == 'nvls':
+            self.world = VmmSymmetricWorld(self.device)
+
+            def symmetric_alloc(numel, dtype, device):
+                # the parameter arena itself lives in multicast-bound symmetric memory: the kernel
+                # all-gathers the updated slices straight into every replica's parameters
+                self._z_buf = self.world.alloc('ar.z', int(numel) * 4)
+                return self._z_buf.local.view(dtype)
+            self.arena = FlatArena(params, device=self.device, allocator=symmetric_alloc)
+        else:
+            self.arena = FlatArena(params, device=self.device)
         self.arena.adopt(params)
         if world_size > 1:          # AR replicas must start identical
             dist.broadcast(self.arena.flat, src=0)
@@ -53,9 +77,9 @@ class AllReduceDataParallel(Module):
                 dist.broadcast(b.data, src=0)
         C = native.load()
         self.C = C
-        from .symmetric import LocalWorld, SymmetricWorld
-        self.world = (SymmetricWorld(self.device) if world_size > 1
-                      else LocalWorld(1, [self.device.index]).view(0))
+        if transport != 'nvls':
+            self.world = (SymmetricWorld(self.device) if world_size > 1
+                          else LocalWorld(1, [self.device.index]).view(0))
         n = self.arena.total
         esize = 4 if grad_dtype == torch.float32 else 2
         self._grad_buf = self.world.alloc('ar.grad', n * esize)
@@ -63,7 +87,8 @@ class AllReduceDataParallel(Module):
         self.grad_flat.zero_()
         self.arena.bind_grads(params, self.grad_flat)
         self.momentum = self.arena.new_buffer()
-        self.pad = self.world.alloc('ar.pad', C.PAD_BYTES)
+        self.pad = (self.world.alloc('ar.pad', C.PAD_BYTES, multicast=False) if transport == 'nvls'
+                    else self.world.alloc('ar.pad', C.PAD_BYTES))
         self.state = torch.zeros(C.STATE_BYTES, dtype=torch.uint8, device=self.device)
         self.state.view(torch.float32)[C.STATE_OFF_PSW // 4: C.STATE_OFF_PSW // 4 + 2] = 1.0
         self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
@@ -81,6 +106,11 @@ class AllReduceDataParallel(Module):
         if grid is None:
             grid = min(self.ctx.max_grid(), 2 * sms)
         self.grid = int(max(1, min(grid, n // C.CHUNK)))
+        if transport == 'nvls':
+            per_rank = -(-(n // C.CHUNK) // self.world.world)          # chunks of one rank's slice
+            self.grid = int(max(1, min(self.grid, C.nvls_max_grid(self.device.index), per_rank)))
+            self._z_mc = self._z_buf.mc.view(torch.float32)[:n]
+            self._g_mc = self._grad_buf.mc.view(grad_dtype)[:n]
         self.steps = 0
         torch.cuda.synchronize(self.device)
         self.world.barrier()
@@ -104,6 +134,13 @@ class AllReduceDataParallel(Module):
             dist.all_reduce(self.grad_flat)
             self.set_hyper(*self._hyper_cache[:4], grad_scale=1.0 / self.world_size)
             self.ctx.step(C.F_SGD | C.F_ZERO_GRAD | C.F_PHASE1 | C.F_NO_ROTATE, self.grid)
+        elif self.transport == 'nvls':
+            # in-switch reduce of the owned slice + sharded SGD + multicast all-gather; the kernel
+            # also clears the consumed gradient slice on every rank (multimem.st of zeros)
+            C.nvls_allreduce(self.arena.flat, self._z_mc, self._g_mc, self.momentum, self.pad.table,
+                             self.state, self.hyper, self.world.rank, self.world.world, self._timeout_s,
+                             1.0, True, self.grid)
+            self.steps += 1
         else:
             self.ctx.allreduce_sgd(self._grad_buf.table, 0, self.grid)
             C.zero_(self.grad_flat)

@@ -268,14 +268,7 @@ class GossipDataParallel(Module):
 
         self.module = module
         self._module_copies = [self.module]
-        if len(self.device_ids) > 1:
-            # the reference's DataParallel-style mode (one process driving 8 GPUs with
-            # replicate / broadcast_coalesced / reduce_add_coalesced, gossip/distributed.py:
-            # 87-99, 256-276, 523-549) is superseded by one process per GPU: intra-node
-            # replicas are ranks of the same gossip world or use nprocs_per_node > 1
-            raise NotImplementedError(
-                'single-process multi-GPU replicas are not supported: launch one rank per GPU '
-                '(torchrun --nproc-per-node N) or use nprocs_per_node for hierarchical groups')
+        self._replica_arenas = []       # single-process multi-GPU mode: (arena, grad_flat) per replica
         first_param_dtype = first_param.dtype
 
         # -- communication device / transport ------------------------------- #
@@ -309,11 +302,22 @@ class GossipDataParallel(Module):
         params = [p for p in module.parameters()]
         by_dtype = group_by_dtype(params)
         self._arenas: Dict[torch.dtype, FlatArena] = {}
+        self._hier = self._make_local_nvls_group(by_dtype, on_cuda, first_param.device)
         for dtype, group in by_dtype.items():
-            arena = FlatArena(group, device=group[0].device)
+            alloc = self._hier.arena_allocator if (self._hier is not None and dtype == torch.float32) else None
+            arena = FlatArena(group, device=group[0].device, allocator=alloc)
             arena.adopt(group)
             self._arenas[dtype] = arena
         self._params_by_dtype = by_dtype
+        self._hier_grad = None
+        if self._hier is not None:
+            # the flat gradient of the local ranks lives in multicast-bound symmetric memory so
+            # that the local-node average is one in-switch reduction (FusedGossipSGD reuses it)
+            self._hier_grad = self._hier.finish(self._arenas[torch.float32])
+            self._arenas[torch.float32].bind_grads(by_dtype[torch.float32], self._hier_grad)
+
+        if len(self.device_ids) > 1:
+            self._build_local_replicas()
 
         all_fp32 = list(by_dtype.keys()) == [torch.float32]
         if transport == 'auto':
@@ -496,7 +500,112 @@ class GossipDataParallel(Module):
             inputs, kwargs = (inputs,), (kwargs,)
         if self.nprocs_per_node > 1:
             self._sync_params_multiprocess()
-        return self.module(*inputs[0], **kwargs[0])
+        if len(self.device_ids) == 1 or len(self._module_copies) == 1:
+            return self.module(*inputs[0], **kwargs[0])
+        # single-process multi-GPU (reference :253-276): master -> replicas, one thread per GPU
+        self._sync_params()
+        n = min(len(inputs), len(self._module_copies))
+        outputs = self.parallel_apply(self._module_copies[:n], inputs[:n], kwargs[:n])
+        return self.gather(outputs, self.output_device)
+
+    # ------------------------------------------------------------------ #
+    # single-process multi-GPU replicas (reference :87-99, 231-276, 523-549; N10)
+    # ------------------------------------------------------------------ #
+    def _build_local_replicas(self):
+        """One process drives ``device_ids`` (the reference's default launch mode: 8 GPUs per
+        process).  Each extra GPU gets a deep copy of the module whose parameters are re-homed
+        into ONE flat arena with ONE flat gradient buffer, so that the reference's
+        ``broadcast_coalesced`` is a single peer-to-peer DMA copy of the arena per replica and
+        its ``reduce_add_coalesced`` is a single kernel on the master GPU that sums the
+        replicas' flat gradients with 16-byte P2P loads (``_C.peer_reduce_``).  Gossip runs on
+        ``device_ids[0]``'s parameters, exactly as in the reference."""
+        import copy
+        assert list(self._params_by_dtype.keys()) == [torch.float32] or \
+            len(self._params_by_dtype) == 1, 'multi-GPU replicas need single-dtype parameters'
+        dtype = next(iter(self._arenas))
+        master = self._arenas[dtype]
+        params0 = self._params_by_dtype[dtype]
+        self._master_grad = master.new_buffer()
+        master.bind_grads(params0, self._master_grad)
+        self._replica_arenas = [(master, self._master_grad)]
+        for dev_idx in self.device_ids[1:]:
+            dev = torch.device('cuda', dev_idx)
+            rep = copy.deepcopy(self.module).to(dev)
+            rparams = [p for p in rep.parameters()]
+            arena = FlatArena(rparams, device=dev)
+            arena.adopt(rparams)
+            gflat = arena.new_buffer()
+            arena.bind_grads(rparams, gflat)
+            self._module_copies.append(rep)
+            self._replica_arenas.append((arena, gflat))
+        for m in self._module_copies[1:]:
+            m.train(self.module.training)
+
+    def _sync_params(self):
+        """master parameters / buffers -> every local replica (reference :256-276)"""
+        master, _ = self._replica_arenas[0]
+        cur = torch.cuda.current_stream(master.flat.device)
+        for (arena, _), rep in zip(self._replica_arenas[1:], self._module_copies[1:]):
+            with torch.cuda.device(arena.flat.device):
+                s = torch.cuda.current_stream(arena.flat.device)
+                s.wait_stream(cur)
+                arena.flat.copy_(master.flat, non_blocking=True)        # one P2P DMA copy
+                for b_m, b_r in zip(self.module.buffers(), rep.buffers()):
+                    b_r.copy_(b_m, non_blocking=True)
+
+    def _master_grad_flat(self):
+        """the flat buffer the master's ``p.grad`` views live in, or None if an optimizer
+        replaced them (``zero_grad(set_to_none=True)``)"""
+        dtype = next(iter(self._arenas))
+        opt = self._fused_optimizer
+        cand = opt.grad_flat[dtype] if (opt is not None and not self._twin) else self._master_grad
+        arena = self._arenas[dtype]
+        for p, v in zip(self._params_by_dtype[dtype], arena.views_of(cand)):
+            if p.requires_grad:
+                return cand if (p.grad is not None and p.grad.data_ptr() == v.data_ptr()) else None
+        return None
+
+    def _reduce_local_grads(self):
+        """sum of the replicas' flat gradients -> the master's gradient (reference :523-549)"""
+        from ..ops import native
+        dtype = next(iter(self._arenas))
+        arena0 = self._arenas[dtype]
+        dev0 = arena0.flat.device
+        cur = torch.cuda.current_stream(dev0)
+        for _, g in self._replica_arenas[1:]:
+            cur.wait_stream(torch.cuda.current_stream(g.device))
+        replica_grads = [g for _, g in self._replica_arenas[1:]]
+        g0 = self._master_grad_flat()
+        fused = native.available() and arena0.flat.is_cuda
+        if g0 is not None:
+            if fused:
+                native.load().peer_reduce_(g0, [g0] + replica_grads, 1.0)     # in place, ONE kernel
+            else:
+                for g in replica_grads:
+                    g0.add_(g.to(dev0))
+        else:
+            # foreign per-tensor gradients on the master: reduce the replicas into a scratch arena,
+            # then one add per tensor
+            if getattr(self, '_grad_scratch', None) is None:
+                self._grad_scratch = arena0.new_buffer()
+            sc = self._grad_scratch
+            if fused:
+                native.load().peer_reduce_(sc, replica_grads, 1.0)
+            else:
+                sc.zero_()
+                for g in replica_grads:
+                    sc.add_(g.to(dev0))
+            for p, v in zip(self._params_by_dtype[dtype], arena0.views_of(sc)):
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.add_(v)
+        for _, g in self._replica_arenas[1:]:
+            with torch.cuda.device(g.device):
+                torch.cuda.current_stream(g.device).wait_stream(cur)
+                g.zero_()
 
     def scatter(self, inputs, kwargs, device_ids):
         from torch.nn.parallel.scatter_gather import scatter_kwargs
@@ -510,11 +619,30 @@ class GossipDataParallel(Module):
         from torch.nn.parallel.scatter_gather import gather
         return gather(outputs, output_device, dim=0)
 
+    def _make_local_nvls_group(self, by_dtype, on_cuda, device):
+        """hierarchical mode (``nprocs_per_node > 1``) on the kernel plane: the local ranks of a
+        node share a VMM symmetric world with multicast mappings; None when unavailable (CPU,
+        gloo-only hosts, no NVSwitch multicast) -> the c10d collectives of the reference."""
+        if not (self.nprocs_per_node > 1 and on_cuda and dist.is_initialized()
+                and self.local_node_group is not None and torch.float32 in by_dtype):
+            return None
+        from .symmetric import VmmSymmetricWorld
+        ok = torch.tensor([1 if VmmSymmetricWorld.supported(device) else 0], device=device
+                          if dist.get_backend() == 'nccl' else 'cpu')
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.local_node_group)
+        if int(ok.item()) == 0:
+            return None
+        return _LocalNvlsGroup(self, device)
+
     def _sync_params_multiprocess(self):
         """Node master -> local ranks (reference :278-296); the parameters are
-        one flat arena per dtype so this is one broadcast per dtype."""
+        one flat arena per dtype so this is one broadcast per dtype -- on the kernel plane a
+        ``multimem.st`` broadcast through the switch (``sgp_nvls_bcast_kernel``)."""
         src = self.dist_config['rank'] * self.nprocs_per_node
-        for arena in self._arenas.values():
+        for dtype, arena in self._arenas.items():
+            if self._hier is not None and dtype == torch.float32:
+                self._hier.broadcast_params(arena)
+                continue
             dist.broadcast(arena.flat, src=src, group=self.local_node_group)
         buffers = [b.data for b in self.module.buffers()]
         if buffers:
@@ -727,7 +855,13 @@ class GossipDataParallel(Module):
 
     def __make_backward_hook(self):
         def hook(*unused):
-            if self.nprocs_per_node > 1:
+            if len(self._module_copies) > 1:
+                self._reduce_local_grads()
+            if self.nprocs_per_node > 1 and self._hier is not None and self._hier.grads_in_place(self):
+                # local-node gradient average: ONE in-switch all-reduce of the flat symmetric
+                # gradient buffer (multimem.ld_reduce + multimem.st), scaled by 1/nprocs
+                self._hier.allreduce_grads()
+            elif self.nprocs_per_node > 1:
                 grads = [p.grad.data for p in self.module.parameters()
                          if p.requires_grad and p.grad is not None]
                 for g in grads:
@@ -756,6 +890,65 @@ class GossipDataParallel(Module):
                 self._flush_pending()     # deferred SGD must land before forward
             self.unbias()
         return hook
+
+
+class _LocalNvlsGroup(object):
+    """NVLS data plane of one node's local ranks (hierarchical mode, reference :62-80, 278-296,
+    551-562): parameter arena + flat gradient in multicast-bound symmetric memory, a signal pad,
+    and the two launches -- ``multimem.st`` parameter broadcast from the node master and the
+    in-switch gradient all-reduce."""
+
+    def __init__(self, owner, device):
+        from ..ops import native
+        from .symmetric import VmmSymmetricWorld
+        self.C = native.load()
+        self.owner = owner
+        self.device = device
+        self.world = VmmSymmetricWorld(device, owner.local_node_group)
+        self.tag = 'hier%d' % owner._instance_id
+        self.z_buf = None
+        self.g_buf = None
+        self.timeout_s = owner._timeout_s
+
+    def arena_allocator(self, numel, dtype, device):
+        self.z_buf = self.world.alloc(self.tag + '.z', int(numel) * 4)
+        return self.z_buf.local.view(dtype)
+
+    def finish(self, arena):
+        C = self.C
+        n = arena.total
+        self.n = n
+        self.g_buf = self.world.alloc(self.tag + '.g', n * 4)
+        self.pad = self.world.alloc(self.tag + '.pad', C.PAD_BYTES, multicast=False)
+        self.state = torch.zeros(C.STATE_BYTES, dtype=torch.uint8, device=self.device)
+        self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
+        self.z_mc = self.z_buf.mc.view(torch.float32)[:n]
+        self.g_mc = self.g_buf.mc.view(torch.float32)[:n]
+        self.grad_flat = self.g_buf.local.view(torch.float32)[:n]
+        self.grad_flat.zero_()
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        per_rank = -(-(n // C.CHUNK) // self.world.world)
+        self.grid = int(max(1, min(2 * sms, C.nvls_max_grid(self.device.index), per_rank)))
+        torch.cuda.synchronize(self.device)
+        self.world.barrier()
+        return self.grad_flat
+
+    def grads_in_place(self, owner) -> bool:
+        """are the module's ``.grad`` tensors still views of the symmetric flat buffer?"""
+        arena = owner._arenas[torch.float32]
+        for p, v in zip(owner._params_by_dtype[torch.float32], arena.views_of(self.grad_flat)):
+            if p.requires_grad:
+                return p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+        return False
+
+    def broadcast_params(self, arena):
+        self.C.nvls_bcast(self.z_mc, arena.flat, self.pad.table, self.state, self.world.rank,
+                          self.world.world, 0, self.timeout_s, self.grid)
+
+    def allreduce_grads(self):
+        self.C.nvls_allreduce(None, None, self.g_mc, None, self.pad.table, self.state, self.hyper,
+                              self.world.rank, self.world.world, self.timeout_s,
+                              1.0 / self.world.world, False, self.grid)
 
 
 def _native_ok() -> bool:

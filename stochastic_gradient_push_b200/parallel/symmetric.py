@@ -29,7 +29,7 @@ from ..ops import native
 
 
 class _Buffer(object):
-    __slots__ = ('name', 'nbytes', 'local', 'peers', 'table')
+    __slots__ = ('name', 'nbytes', 'local', 'peers', 'table', 'mc', 'vmm')
 
     def __init__(self, name, nbytes):
         self.name = name
@@ -37,6 +37,8 @@ class _Buffer(object):
         self.local = None      # uint8 tensor owned by this rank
         self.peers = None      # list of uint8 tensors (index = rank)
         self.table = None      # int64 device tensor of base pointers
+        self.mc = None         # uint8 tensor over the MULTICAST mapping (VmmSymmetricWorld), or None
+        self.vmm = None        # the native VmmBuffer that owns the physical memory
 
 
 class SymmetricWorld(object):
@@ -86,6 +88,61 @@ class SymmetricWorld(object):
     def barrier(self):
         if self.world > 1:
             dist.barrier(group=self.group)
+
+
+class VmmSymmetricWorld(SymmetricWorld):
+    """Symmetric allocator on the CUDA virtual-memory-management API with an NVSwitch multicast
+    view (``_C.VmmBuffer``, csrc/vmm_symm.cpp): ``alloc()`` returns a buffer whose ``peers`` /
+    ``table`` are ordinary unicast P2P mappings (same contract as :class:`SymmetricWorld`) and
+    whose ``mc`` is a tensor over the multicast address -- ``multimem.ld_reduce`` reads through it
+    are summed inside the switch, ``multimem.st`` writes land in every GPU.  POSIX file
+    descriptors of the allocations travel as integers over the c10d control plane and are
+    duplicated with ``pidfd_getfd`` (single host, one NVLink domain)."""
+
+    @staticmethod
+    def supported(device=None) -> bool:
+        if not (torch.cuda.is_available() and native.available()):
+            return False
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        caps = native.load().vmm_caps(int(dev))
+        return bool(caps.get('multicast') and caps.get('posix_fd'))
+
+    def alloc(self, name: str, nbytes: int, multicast: bool = True) -> _Buffer:
+        assert name not in self.buffers
+        C = self._C
+        buf = _Buffer(name, nbytes)
+        vb = C.VmmBuffer(int(nbytes), self.device.index, self.world)
+        buf.vmm = vb
+        buf.local = vb.local()
+        gathered = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(gathered, (vb.pid(), vb.fd(), int(nbytes)), group=self.group)
+        buf.peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                buf.peers.append(buf.local)
+            else:
+                pid, fd, nb = gathered[r]
+                assert nb == nbytes, 'symmetric allocations must have equal size'
+                buf.peers.append(vb.open_peer(int(pid), int(fd)))
+        buf.table = torch.tensor([t.data_ptr() for t in buf.peers], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)            # every fd has been duplicated by every peer
+        if multicast and self.world > 1:
+            info = [None]
+            if self.rank == 0:
+                info[0] = (vb.pid(), vb.mc_create())
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast_object_list(info, src=src, group=self.group)
+            if self.rank != 0:
+                vb.mc_import(int(info[0][0]), int(info[0][1]))
+            dist.barrier(group=self.group)
+            vb.mc_add_device()
+            dist.barrier(group=self.group)            # all devices joined before anybody binds
+            buf.mc = vb.mc_bind_and_map()
+            dist.barrier(group=self.group)
+        self.buffers[name] = buf
+        return buf
 
 
 class LocalWorld(object):

@@ -94,34 +94,50 @@ def test_allreduce_world1_matches_torch_sgd():
         torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
 
 
-def test_single_process_multi_gpu_is_rejected_with_guidance():
+@pytest.mark.parametrize('fused', [False, True])
+def test_single_process_multi_replica_mode_matches_one_big_batch(fused):
+    """reference launch mode (one process, several GPUs; gossip/distributed.py:87-99, 253-276,
+    523-549): replicas on device_ids, scatter -> parallel_apply -> gather, the replicas' flat
+    gradients summed into the master's by ONE P2P kernel.  With two replicas (both on cuda:0 when
+    only one GPU is visible) the parameter trajectory must equal plain training on the whole
+    batch (sum of per-replica sum-losses == whole-batch sum-loss)."""
+    import copy
     import stochastic_gradient_push_b200 as sgp
-    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
-    net = torch.nn.Linear(4, 4).cuda(0)
-    with pytest.raises(NotImplementedError, match='one rank per GPU'):
-        GossipDataParallel(net, device_ids=[0, 1], rank=0, world_size=1,
-                           graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1))
-
-
-def _train_tiny(compute_dtype, amp, steps=6, graph=False):
-    import stochastic_gradient_push_b200 as sgp
-    from stochastic_gradient_push_b200 import models
     from stochastic_gradient_push_b200.optim import FusedGossipSGD
     from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
-    from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
+    ids = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
     dev = torch.device('cuda', 0)
-    torch.manual_seed(3)
-    net = models.TinyConvNet(width=32).to(dev).to(memory_format=torch.channels_last)
-    model = GossipDataParallel(net, graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1), rank=0,
-                               world_size=1, heartbeat_timeout=20, compute_dtype=compute_dtype)
-    opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
-    tr = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=graph, warmup_iters=2)
-    g = torch.Generator().manual_seed(11)
-    x = torch.randn(32, 3, 32, 32, generator=g).pin_memory()
-    y = torch.randint(0, 10, (32,), generator=g).pin_memory()
-    slots = [tr.step(x, y) for _ in range(steps)]
-    tr.finish()
-    return model, [float(tr.loss_ring[s]) for s in slots]
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).to(dev)
+    ref = copy.deepcopy(net)
+    model = GossipDataParallel(net, device_ids=ids, graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1),
+                               rank=0, world_size=1, heartbeat_timeout=20)
+    assert len(model._module_copies) == 2
+    if fused:
+        opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    for _ in range(5):
+        x = torch.randn(24, 16, device=dev, generator=g)
+        y = torch.randn(24, 4, device=dev, generator=g)
+        out = model(x)
+        assert out.shape == (24, 4) and out.device == dev
+        ((out - y) ** 2).sum().backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False) if not fused else opt.zero_grad()
+        model.transfer_params()
+        model._query_gossip_queue()
+        model._flush_pending()
+        ((ref(x) - y) ** 2).sum().backward()
+        ropt.step()
+        ropt.zero_grad()
+    torch.cuda.synchronize()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
+    # the replica was refreshed from the master at the last forward and has its own arena
+    assert model._replica_arenas[1][0].flat.device.index == ids[1]
 
 
 @pytest.mark.parametrize('graph', [False, True])

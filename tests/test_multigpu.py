@@ -214,7 +214,7 @@ def _adpsgd_consensus(rank, world, seconds):
                                     graph_class=sgp.DynamicBipartiteExponentialGraph,
                                     mixing_class=sgp.UniformMixing, lr=0.0, momentum=0.0,
                                     weight_decay=0.0, nesterov=False, verbose=False,
-                                    heartbeat_timeout=20)
+                                    heartbeat_timeout=20, max_rounds_per_update=None)
     assert model.transport == 'nvlink'
     total0 = torch.tensor([float(rank)], device=dev)
     dist.all_reduce(total0)
@@ -391,3 +391,128 @@ def test_device_barrier_kernel():
     for i in range(3):                            # nobody leaves a barrier before the last arrives
         leave = [out[r][i] for r in range(n)]
         assert max(leave) - min(leave) < 0.04, leave
+
+
+# --------------------------------------------------------------------------- #
+# NVLS: VMM symmetric memory + multicast, multimem.* kernels
+# --------------------------------------------------------------------------- #
+def _nvls_supported():
+    from stochastic_gradient_push_b200.parallel.symmetric import VmmSymmetricWorld
+    return _ngpu() >= 2 and VmmSymmetricWorld.supported(0)
+
+
+def _vmm_world_worker(rank, world):
+    from stochastic_gradient_push_b200.parallel.symmetric import VmmSymmetricWorld
+    dev = torch.device('cuda', rank)
+    sw = VmmSymmetricWorld(dev)
+    buf = sw.alloc('t', 1 << 20)
+    mine = buf.local.view(torch.float32)
+    mine.fill_(float(rank + 1))
+    torch.cuda.synchronize()
+    sw.barrier()
+    # unicast P2P view of every peer + the multicast view exist and alias the right memory
+    seen = [float(buf.peers[r].view(torch.float32)[5].item()) for r in range(world)]
+    assert buf.mc is not None and buf.mc.numel() == buf.local.numel()
+    sw.barrier()
+    return seen
+
+
+def test_vmm_symmetric_world_maps_peers_and_multicast():
+    if not _nvls_supported():
+        pytest.skip('no NVSwitch multicast')
+    n = min(_ngpu(), 4)
+    out = run_distributed(_vmm_world_worker, n, backend='nccl', timeout=200)
+    for seen in out:
+        assert seen == [float(r + 1) for r in range(n)]
+
+
+def _nvls_ar_worker(rank, world, grad_dtype, steps):
+    import copy
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.allreduce import AllReduceDataParallel
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.ReLU(), torch.nn.Linear(256, 40)).to(dev)
+    ref = copy.deepcopy(net)
+    ar = AllReduceDataParallel(net, rank=rank, world_size=world, transport='nvls',
+                               grad_dtype=torch.bfloat16 if grad_dtype == 'bf16' else torch.float32)
+    assert ar.transport == 'nvls'
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    ar.set_hyper(0.1, 0.9, 1e-4, True)
+    g = torch.Generator(device='cuda').manual_seed(100 + rank)
+    for _ in range(steps):
+        x = torch.randn(32, 64, device=dev, generator=g)
+        ar(x).square().mean().backward()
+        # reference: average of the ranks' gradients (as the kernel will see them), plain SGD
+        gflat = ar.grad_flat.float().clone()
+        dist.all_reduce(gflat)
+        gflat /= world
+        ar.allreduce_step()
+        opt.zero_grad()
+        for p, v in zip(ref.parameters(), ar.arena.views_of(gflat)):
+            p.grad = v.clone()
+        opt.step()
+        torch.cuda.synchronize()
+        ar.check()
+        assert float(ar.grad_flat.float().abs().max()) == 0.0       # cleared on every rank by multimem.st
+    tol = dict(rtol=1e-4, atol=1e-5) if grad_dtype == 'fp32' else dict(rtol=2e-2, atol=2e-3)
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q, **tol)
+    # replicas are bit-identical (every rank received the same multicast values)
+    flat = ar.arena.flat.clone()
+    others = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(others, flat)
+    assert all(torch.equal(o, others[0]) for o in others)
+    return True
+
+
+@pytest.mark.parametrize('grad_dtype', ['fp32', 'bf16'])
+def test_nvls_allreduce_sgd_matches_torch_sgd(grad_dtype):
+    if not _nvls_supported():
+        pytest.skip('no NVSwitch multicast')
+    n = min(_ngpu(), 8)
+    assert all(run_distributed(_nvls_ar_worker, n, grad_dtype, 5, backend='nccl', timeout=300))
+
+
+def _hier_nvls_worker(rank, world, steps):
+    """world = ONE node of `world` local ranks (nprocs_per_node = world): the gossip world has a
+    single (peer-less) agent, so the result must equal single-process SGD on the mean gradient."""
+    import copy
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(32, 128), torch.nn.Tanh(), torch.nn.Linear(128, 8)).to(dev)
+    ref = copy.deepcopy(net)
+    if rank != 0:
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(1.0)                  # only the node master's parameters count (broadcast)
+    model = GossipDataParallel(net, rank=rank, world_size=world, nprocs_per_node=world,
+                               graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1), heartbeat_timeout=30)
+    assert model._hier is not None, 'hierarchical mode did not get its NVLS group'
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+    gens = [torch.Generator(device='cuda').manual_seed(7 + r) for r in range(world)]
+    for _ in range(steps):
+        xs = [torch.randn(16, 32, device=dev, generator=g) for g in gens]
+        model(xs[rank]).square().mean().backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        model.transfer_params()
+        model._query_gossip_queue()
+        torch.stack([ref(x).square().mean() for x in xs]).mean().backward()
+        ropt.step()
+        ropt.zero_grad()
+    # one more forward: parameters of the master have been multicast to everyone
+    model(xs[rank])
+    torch.cuda.synchronize()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
+    return True
+
+
+def test_hierarchical_mode_runs_on_nvls_kernels():
+    if not _nvls_supported():
+        pytest.skip('no NVSwitch multicast')
+    assert all(run_distributed(_hier_nvls_worker, 2, 4, backend='nccl', timeout=300))
