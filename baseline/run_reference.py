@@ -71,6 +71,107 @@ class _Stopwatch(object):
         return False
 
 
+class _TimedRegionDone(Exception):
+    pass
+
+
+def main_adpsgd(args, rank, world, master_port, torch, dist):
+    """AD-PSGD comparator: the reference's own ``gossip_sgd_adpsgd.py`` (copied unmodified into
+    ``baseline/_ref/bin`` next to ``gossip_sgd.py``; its setup.py installs only the latter) ->
+    ``main()`` -> ``train()`` with ``gossip.BilatGossipDataParallel``: two worlds per rank, the
+    training process on ``master_port + 1`` and the forked gossip PROCESS on ``master_port``
+    (``gossip_sgd_adpsgd.py:695``, ``gossip/ad_psgd.py:280-284``), CUDA-IPC shared parameter /
+    gradient tensors between them.  Substitutions: synthetic loader (= stopwatch), the one-word
+    ``accuracy`` fix, the ``forkserver`` start method its ``__main__`` block sets."""
+    import torch.multiprocessing as mp
+    script = os.path.join(REF, 'bin', 'gossip_sgd_adpsgd.py')
+    if not os.path.isfile(script):
+        unavailable('baseline/_ref/bin/gossip_sgd_adpsgd.py missing (cp from the reference tree)')
+    mp.set_start_method('forkserver', force=True)
+    spec = importlib.util.spec_from_file_location('ref_gossip_sgd_adpsgd', script)
+    ref = importlib.util.module_from_spec(spec)
+    ckpt = tempfile.mkdtemp(prefix='ref_ckpt_') + '/'
+    shared = '/tmp/ref_adpsgd_counter_%s.txt' % master_port
+    sys.argv = ['gossip_sgd_adpsgd.py', '--bilat', 'True', '--graph_type', '1', '--shared_fpath', shared,
+                '--batch_size', str(args.batch_size), '--lr', '0.1', '--num_dataloader_workers', '0',
+                '--num_epochs', '1', '--nesterov', 'True', '--warmup', 'True', '--seed', '1',
+                '--schedule', '30', '0.1', '60', '0.1', '80', '0.1', '--print_freq', '100',
+                '--verbose', 'False', '--train_fast', 'True', '--checkpoint_dir', ckpt,
+                '--dataset_dir', '/nonexistent', '--backend', 'nccl',
+                '--network_interface_type', 'infiniband', '--master_port', master_port, '--tag', 'ref_']
+    spec.loader.exec_module(ref)
+    warmup, steps, bs = args.warmup, args.steps, args.batch_size
+    watch = _Stopwatch(warmup, steps)
+    h2d_bytes = bs * 3 * 224 * 224 * 4 + bs * 8
+
+    class SyntheticLoader(object):
+        def __init__(self):
+            g = torch.Generator().manual_seed(1234 + rank)
+            self.pool = [(torch.randn(bs, 3, 224, 224, generator=g).pin_memory(),
+                          torch.randint(0, 1000, (bs,), generator=g).pin_memory()) for _ in range(4)]
+
+        def __len__(self):
+            return 5005
+
+        def __iter__(self):
+            for i in range(warmup + steps + 1):
+                if watch.mark(i, torch, dist):
+                    raise _TimedRegionDone()      # leave the reference's epoch loop
+                yield self.pool[i % len(self.pool)]
+
+    class _Sampler(object):
+        def set_epoch(self, e):
+            pass
+
+    ref.make_dataloader = lambda a, train=True: ((SyntheticLoader(), _Sampler()) if train else [])
+
+    def accuracy(output, target, topk=(1,)):
+        with torch.no_grad():
+            maxk = max(topk)
+            _, pred = output.topk(maxk, 1, True, True)
+            pred = pred.t()
+            correct = pred.eq(target.view(1, -1).expand_as(pred))
+            return [correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / target.size(0))
+                    for k in topk]
+
+    ref.accuracy = accuracy
+    t_all = time.time()
+    try:
+        ref.main()
+    except _TimedRegionDone:
+        pass
+    torch.cuda.synchronize()
+    if watch.ms is None:
+        unavailable('reference AD-PSGD loop ended before the timed region completed')
+    ms = torch.tensor([watch.ms], device='cuda')
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    value = bs * world * steps / (ms / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'resnet50_adpsgd_images_per_sec', 'value': round(value, 2),
+            'unit': 'images/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': round(ms / steps, 4), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32 (cuDNN TF32 conv default)', 'data': 'synthetic',
+            'value_is_e2e': True,
+            'config': {'model': 'resnet50 (torchvision, reference init_model)', 'algorithm': 'adpsgd',
+                       'per_gpu_batch': bs, 'global_batch': bs * world, 'image': '3x224x224',
+                       'parallelism': 'dp%d' % world,
+                       'entry': 'baseline/_ref/bin/gossip_sgd_adpsgd.py main()->train(), stock; gossip '
+                                'process + second process group as in the reference'},
+            'e2e': {'value': round(value, 2), 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': 12},
+            'gpu_launches': 0, 'wall_s': round(time.time() - t_all, 1)}))
+    sys.stdout.flush()
+    try:
+        dist.barrier()
+    except Exception:
+        pass
+    for child in mp.active_children():           # the forked gossip process never exits on its own
+        child.terminate()
+    os._exit(0)
+
+
 def main(args):
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -95,13 +196,15 @@ def main(args):
     import gossip
     assert os.path.abspath(gossip.__file__).startswith(REF), gossip.__file__
 
+    algo = args.algo
+    if world == 1:
+        algo = 'ar'
+    if algo == 'adpsgd':
+        return main_adpsgd(args, rank, world, master_port, torch, dist)
     spec = importlib.util.spec_from_file_location(
         'ref_gossip_sgd', os.path.join(REF, 'bin', 'gossip_sgd.py'))
     ref = importlib.util.module_from_spec(spec)
     ckpt = tempfile.mkdtemp(prefix='ref_ckpt_') + '/'
-    algo = args.algo
-    if world == 1:
-        algo = 'ar'
     argv = ['gossip_sgd.py', '--batch_size', str(args.batch_size), '--lr', '0.1',
             '--num_dataloader_workers', '0', '--num_epochs', '1',
             '--nesterov', 'True', '--warmup', 'True', '--seed', '1',

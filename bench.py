@@ -60,6 +60,9 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--autocast', action='store_true',
                     help='bf16 via torch.autocast instead of the bf16 shadow-weight twin')
+    ap.add_argument('--ar-transport', default='auto', choices=['auto', 'nvls', 'p2p', 'nccl'],
+                    help='AllReduce-SGD data plane: NVLS multimem kernel (auto when supported), the '
+                         'one-shot P2P kernel, or NCCL all-reduce + fused SGD')
     ap.add_argument('--adpsgd-rounds', type=int, default=4,
                     help='AD-PSGD: bilateral rounds a rank may start per applied gradient (0 = unbounded)')
     ap.add_argument('--skip-e2e', action='store_true')
@@ -144,10 +147,10 @@ def _build(args, dtype, bs, rank, world, dev):
     lr = 0.1 * bs * world / 256
     if args.algo == 'ar':
         from stochastic_gradient_push_b200.parallel.allreduce import AllReduceDataParallel, ARTrainer
-        model = AllReduceDataParallel(net)
+        model = AllReduceDataParallel(net, transport=args.ar_transport)
         trainer = ARTrainer(model, lr=lr, momentum=0.9, weight_decay=1e-4, nesterov=True,
                             amp_dtype=amp, use_cuda_graph=not args.no_graph)
-        return net, model, trainer, 'all-reduce'
+        return net, model, trainer, 'all-reduce (%s)' % model.transport
     if args.algo == 'adpsgd':
         from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel, make_bilat_trainer
         model = BilatGossipDataParallel(net, rank=rank, world_size=world,
