@@ -135,6 +135,20 @@ def resolve_env(args):
     return args
 
 
+def resolve_backend(args) -> str:
+    """``--backend mpi`` (reference ``gossip_sgd.py:127-129, 600-602``): ranks come from the
+    ``mpirun`` environment (``OMPI_COMM_WORLD_*``, see :func:`resolve_env`).  A PyTorch built with
+    MPI uses the MPI process group as in the reference; otherwise MPI stays the *launcher* and the
+    control plane is a TCP rendezvous (MASTER_ADDR / MASTER_PORT, exported by the job script) over
+    nccl (CUDA) or gloo (CPU).  Either way the data plane on one NVLink domain is the kernel
+    transport, which never touches the process group."""
+    if args.backend != 'mpi':
+        return args.backend
+    if dist.is_mpi_available():
+        return 'mpi'
+    return 'nccl' if (args.device == 'cuda' and dist.is_nccl_available()) else 'gloo'
+
+
 def finalize_args(args, adpsgd=False):
     """Derived settings + process-group / graph / mixing construction."""
     resolve_env(args)
@@ -177,7 +191,7 @@ def finalize_args(args, adpsgd=False):
     # master_port and master_port+1 because its gossip PROCESS owns a second world)
     os.environ['MASTER_PORT'] = str(args.master_port)
     if not dist.is_initialized() and args.world_size > 1:
-        dist.init_process_group(backend=args.backend, world_size=args.world_size, rank=args.rank)
+        dist.init_process_group(backend=resolve_backend(args), world_size=args.world_size, rank=args.rank)
         dist.barrier()        # create the communicator now, not >5 min apart (reference :678-682)
 
     args.graph, args.mixing = None, None

@@ -67,7 +67,12 @@ struct __align__(128) SgpState {
     uint32_t bilat_published;  // 1: this rank's snapshot of the current round is in the outbox
     uint32_t bilat_budget;     // rounds this rank may still START before its next gradient arrives
     uint32_t bilat_enabled;    // 0: gossip disabled (an in-flight round still completes)
-    uint32_t _pad[17];
+    // soft heartbeat: a wait that exceeds soft_timeout_us is COUNTED (and keeps waiting until the
+    // hard timeout); the host logs "gossip round delayed, still waiting" -- the one-sided
+    // analogue of the reference re-queueing an interrupted round (gossip/distributed.py:358-364)
+    uint32_t soft_timeout_us;  // 0 = off
+    uint32_t soft_timeouts;    // waits that went past the soft deadline (monotonic)
+    uint32_t _pad[15];
 };
 
 // ---- hyper-parameters (device resident so CUDA graphs can retarget them) ----
@@ -222,14 +227,21 @@ __device__ __forceinline__ bool spin_wait_geq(const uint32_t* flag, uint32_t wan
                                               uint32_t err_code) {
     if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
     const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long soft_ns = (unsigned long long)(*((volatile uint32_t*)&st->soft_timeout_us)) * 1000ull;
+    bool soft_hit = false;
     uint32_t polls = 0;
     while (true) {
         if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
         if ((++polls & 63u) == 0u) {
             if (*((volatile uint32_t*)&st->status) != SGP_OK) return false;
-            if (globaltimer_ns() - t0 > timeout_ns) {
+            const unsigned long long waited = globaltimer_ns() - t0;
+            if (waited > timeout_ns) {
                 atomicCAS(&st->status, (uint32_t)SGP_OK, err_code);
                 return false;
+            }
+            if (soft_ns != 0ull && !soft_hit && waited > soft_ns) {
+                soft_hit = true;                    // counted once per wait; keep waiting
+                atomicAdd(&st->soft_timeouts, 1u);
             }
         }
         __nanosleep(64);

@@ -291,6 +291,25 @@ sgp_step_kernel(const SgpArgs a)
                     }
                 }
             }
+            else if (!(flags & SGP_F_SELF_FROM_Z) && (flags & SGP_F_PHASE1)) {
+                // an in-neighbour timed out: "every in-message of this round was lost" -- de-bias the
+                // numerator this CTA published (a valid push-sum state) instead of leaving the
+                // pre-SGD parameters behind; the sticky status word makes the host raise
+                const float inv_own = 1.f / w1;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        const float4 zv = mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first),
+                                               inv_own);
+                        st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                        if (flags & SGP_F_SHADOW)
+                            st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    }
+                }
+            }
             __syncthreads();     // s_ok / s_wn are rewritten by the next segment
         }
     }

@@ -66,7 +66,7 @@ class GossipEngine(object):
                  with_residual: bool = False,
                  grid: Optional[int] = None, gather_grid: Optional[int] = None,
                  timeout_s: float = 30.0, name: str = 'sgp', segments: int = 4,
-                 gather_tma: bool = True):
+                 gather_tma: bool = True, soft_timeout_s: Optional[float] = None):
         C = native.load()
         self.C = C
         self.world = world
@@ -95,6 +95,11 @@ class GossipEngine(object):
         self._state_f32 = self.state.view(torch.float32)
         self._state_i32 = self.state.view(torch.int32)
         self._state_f32[C.STATE_OFF_PSW // 4: C.STATE_OFF_PSW // 4 + 2] = 1.0
+        # soft heartbeat (default: a tenth of the hard one): waits that exceed it are counted and
+        # reported by poll() as "delayed, still waiting" -- see SgpState::soft_timeouts
+        soft = timeout_s / 10.0 if soft_timeout_s is None else soft_timeout_s
+        self._state_i32[C.STATE_OFF_SOFT_TIMEOUT_US // 4] = int(min(max(soft, 0.0) * 1e6, 2 ** 31 - 1))
+        self._soft_seen = 0
         self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
         # ring of pinned staging rows: an lr change must not rewrite host memory that an earlier,
         # still-queued async H2D copy is going to read
@@ -261,11 +266,22 @@ class GossipEngine(object):
             self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._status_dev = self._state_i32[self.C.STATE_OFF_STATUS // 4:
                                                self.C.STATE_OFF_STATUS // 4 + 1]
+            self._soft_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._soft_dev = self._state_i32[self.C.STATE_OFF_SOFT_TIMEOUTS // 4:
+                                             self.C.STATE_OFF_SOFT_TIMEOUTS // 4 + 1]
         if torch.cuda.is_current_stream_capturing():
             return
         st = int(self._status_host[0])
+        soft = int(self._soft_host[0])
+        if soft > self._soft_seen:           # a peer was slower than the soft heartbeat; we kept waiting
+            import logging
+            logging.getLogger('sgp_b200').warning(
+                'rank %d: %d gossip wait(s) exceeded the soft heartbeat and were retried (kept '
+                'waiting for the peer)', self.rank, soft - self._soft_seen)
+            self._soft_seen = soft
         if st == 0:
             self._status_host.copy_(self._status_dev, non_blocking=True)
+            self._soft_host.copy_(self._soft_dev, non_blocking=True)
             if blocking:
                 torch.cuda.current_stream(self.device).synchronize()
                 st = int(self._status_host[0])
@@ -286,6 +302,17 @@ class GossipEngine(object):
                      3: 'device barrier timeout'}
             raise RuntimeError('gossip kernel error on rank %d: %s'
                                % (self.rank, names.get(st, 'code %d' % st)))
+
+    @property
+    def soft_timeouts(self) -> int:
+        """waits that exceeded the soft heartbeat so far (synchronises)"""
+        return int(self._state_i32[self.C.STATE_OFF_SOFT_TIMEOUTS // 4].item())
+
+    def clear_status(self):
+        """forget a reported heartbeat failure (after the application decided to carry on)"""
+        self._state_i32[self.C.STATE_OFF_STATUS // 4] = 0
+        if self._status_host is not None:
+            self._status_host.zero_()
 
     @property
     def device_step(self) -> int:

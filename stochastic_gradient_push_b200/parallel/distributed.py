@@ -111,11 +111,15 @@ class _C10dBackend(object):
             store[key] = t
         return t
 
-    def start(self, ps_weight: float, pollable: bool = False):
+    def start(self, ps_weight: float, pollable: bool = False, mix: bool = True):
         """Snapshot x (numerator, NOT yet self-scaled) and post the exchange.
-        Returns the self-loop weight the caller applies locally."""
+        Returns the self-loop weight the caller applies locally.  ``mix=False`` (retry of an
+        interrupted round): the local numerator already carries the self-loop scaling of the
+        failed attempt, so the messages are rebuilt from ``x / self_w`` (== the pre-mix
+        numerator) and the caller must NOT scale again."""
         out_edges, in_edges = self.graph.get_edges()
         self_w, edge_w = self.mixing.scalar_weights([e.dest for e in out_edges])
+        undo = 1.0 if mix else 1.0 / float(self_w)
         reqs, recvs, keep, poll = [], [], [], []
         for dtype, arena in self.arenas.items():
             n = arena.total + 1
@@ -135,7 +139,7 @@ class _C10dBackend(object):
                 if self.comm_device.type == 'cpu' and arena.flat.is_cuda:
                     torch.cuda.current_stream().synchronize()
                 msg[-1] = ps_weight
-                msg.mul_(edge_w[e.dest])
+                msg.mul_(edge_w[e.dest] * undo)
                 if e.dest == e.src:
                     local_add.append(msg)
                 else:
@@ -148,6 +152,11 @@ class _C10dBackend(object):
         if self.graph.is_dynamic_graph():
             self.graph.get_peers(rotate=True)
         return self_w
+
+    def abort(self):
+        """Drop an interrupted round (reference: ``gossiper.clean_msg_buffers_()`` after a
+        RuntimeError in the gossip thread, ``gossip/distributed.py:494-498``)."""
+        self.pending = None
 
     def done(self) -> bool:
         if self.pending is None:
@@ -235,6 +244,7 @@ class GossipDataParallel(Module):
         self._instance_id = _INSTANCES[0]
         self._timeout_s = float(heartbeat_timeout)
         self.exposed_comm_s = 0.0       # c10d data plane: host seconds blocked waiting for peers
+        self.gossip_retries = 0         # interrupted gossip rounds that were re-queued (soft retry)
 
         first_param = next(module.parameters())
         on_cuda = first_param.is_cuda
@@ -774,8 +784,21 @@ class GossipDataParallel(Module):
             return False
         self.ps_numerator()
         t0 = time.time()
-        with tracing.span('gossip.wait+fold'):
-            self._w += c.finish(self._timeout_s)
+        try:
+            with tracing.span('gossip.wait+fold'):
+                self._w += c.finish(self._timeout_s)
+        except RuntimeError as e:
+            # "atomic gossip was interrupted so try again" (reference :358-364, 494-504): the
+            # round is dropped -- nothing of it was folded -- and re-queued with mix=False: the
+            # local share was already scaled when the failed round started, so the retry only
+            # re-sends the out-messages.  (A heartbeat timeout is a NameError and is NOT retried.)
+            self.logger.warning('received runtime error {}; re-queueing the gossip round'.format(e))
+            c.abort()
+            self.gossip_retries += 1
+            self.params_mixed = True
+            self.gossiping = False
+            self.transfer_params(mix=False)
+            return False
         # host time spent blocked on peers = communication NOT hidden behind compute
         self.exposed_comm_s += time.time() - t0
         tracing.counter('exposed_comm_ms', (time.time() - t0) * 1e3)
@@ -798,10 +821,11 @@ class GossipDataParallel(Module):
             self.ps_numerator()
             c = self._c10d
             with tracing.span('gossip.post'):
-                self_w = c.start(self._w, pollable=self.asynch)
-            for arena in self._arenas.values():     # keep the self-loop share
-                arena.flat.mul_(self_w)
-            self._w *= self_w
+                self_w = c.start(self._w, pollable=self.asynch, mix=mix)
+            if mix:
+                for arena in self._arenas.values():     # keep the self-loop share
+                    arena.flat.mul_(self_w)
+                self._w *= self_w
         self.params_mixed = False
         self.gossiping = True
         self._rounds_started += 1

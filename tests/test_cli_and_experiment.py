@@ -228,3 +228,33 @@ def test_cluster_manager_agrees_on_preemption_across_ranks(tmp_path):
     from dist_utils import run_distributed
     out = run_distributed(_signal_worker, 2, str(tmp_path) + '/')
     assert out == [(True, True), (True, True)]
+
+
+def _mpirun_like(nproc, script, args, port, timeout=600):
+    """what `mpirun -np N python gossip_sgd.py --backend mpi` looks like to the script: one process
+    per rank with OMPI_COMM_WORLD_* set (no torchrun variables), MASTER_* exported by the job script"""
+    procs = []
+    for r in range(nproc):
+        env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+        env.update(OMP_NUM_THREADS='1', OMPI_COMM_WORLD_RANK=str(r), OMPI_COMM_WORLD_SIZE=str(nproc),
+                   OMPI_UNIVERSE_SIZE=str(nproc), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, script)] + args, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    return [p.returncode for p in procs], outs
+
+
+def test_backend_mpi_uses_the_mpirun_environment(tmp_path, master_port):
+    """`--backend mpi` (reference gossip_sgd.py:127-129): ranks / world from OMPI_COMM_WORLD_*;
+    without an MPI-enabled PyTorch the control plane falls back to a TCP rendezvous (gloo here)."""
+    a = common.build_parser().parse_args(['--backend', 'mpi'])
+    a.device = 'cpu'
+    want = 'mpi' if torch.distributed.is_mpi_available() else 'gloo'
+    assert common.resolve_backend(a) == want
+    args = [x if x != 'gloo' else 'mpi' for x in COMMON] + [
+        '--push_sum', 'True', '--graph_type', '5', '--num_epochs', '1',
+        '--checkpoint_dir', str(tmp_path) + '/', '--num_itr_ignore', '0']
+    codes, outs = _mpirun_like(2, 'gossip_sgd.py', args, master_port)
+    assert codes == [0, 0], outs[0][-2000:] + outs[1][-2000:]
+    for r in range(2):
+        assert open(str(tmp_path / ('out_r%d_n2.csv' % r))).read().splitlines()[1] == 'World-Size,2'

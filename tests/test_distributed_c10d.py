@@ -330,3 +330,77 @@ def test_heartbeat_timeout_detects_a_slow_peer_and_recovers():
     mean = [(x + y) / 2 for x, y in zip(b0, b1)]
     assert torch.allclose(torch.tensor(a0), torch.tensor(mean), atol=1e-6)
     assert torch.allclose(torch.tensor(a1), torch.tensor(mean), atol=1e-6)
+
+
+# --------------------------------------------------------------------------- #
+# soft retry of an interrupted gossip round (reference gossip/distributed.py:358-364, 494-504)
+# --------------------------------------------------------------------------- #
+class _BrokenOnce(object):
+    """transport wrapper: during round `bad_round` nothing is sent and every receive fails with a
+    RuntimeError -- what a communicator error looks like to the gossip state machine"""
+
+    class _Failed(object):
+        def wait(self):
+            raise RuntimeError('injected communicator failure')
+
+        def is_completed(self):
+            return True
+
+    class _Done(object):
+        def wait(self):
+            return True
+
+        def is_completed(self):
+            return True
+
+    def __init__(self, inner, bad_round):
+        self.inner, self.bad_round, self.round = inner, bad_round, 0
+        self.group = inner.group
+
+    def post_recvs(self, buffers, in_edges):
+        self.round += 1
+        if self.round == self.bad_round:
+            return [self._Failed() for _ in buffers]
+        return self.inner.post_recvs(buffers, in_edges)
+
+    def post_sends(self, msgs, out_edges):
+        if self.round == self.bad_round:
+            return [self._Done() for _ in msgs]
+        return self.inner.post_sends(msgs, out_edges)
+
+    def post_polled_recv(self, buf, in_edge):
+        return self.post_recvs([buf], [in_edge])[0]
+
+
+def _retry_worker(rank, world, bad_round, rounds):
+    import torch.distributed as dist
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    net = nn.Linear(4, 4, bias=False)
+    with torch.no_grad():
+        net.weight.fill_(float(rank + 1))
+    graph = sgp.RingGraph(rank, world, peers_per_itr=1)
+    model = GossipDataParallel(net, graph=graph, rank=rank, world_size=world, verbose=False, push_sum=True)
+    model._c10d.transport = _BrokenOnce(model._c10d.transport, bad_round)
+    model.train()
+    for _ in range(rounds):
+        model.transfer_params()
+        model._query_gossip_queue()
+        if model.gossiping:                   # the interrupted round was re-queued: finish the retry
+            model._query_gossip_queue()
+    model.unbias()
+    total = net.weight.detach().clone() * float(model.ps_weight)
+    dist.all_reduce(total)
+    wsum = torch.tensor([float(model.ps_weight)])
+    dist.all_reduce(wsum)
+    return model.gossip_retries, float(total[0, 0]), float(wsum), float(net.weight[0, 0])
+
+
+def test_interrupted_gossip_round_is_requeued_and_mass_is_conserved():
+    world, rounds = 2, 4
+    out = run_distributed(_retry_worker, world, 2, rounds)
+    for retries, total, wsum, _ in out:
+        assert retries == 1
+        assert abs(total - (1.0 + 2.0)) < 1e-5          # sum of push-sum numerators: conserved
+        assert abs(wsum - world) < 1e-6                 # sum of push-sum weights: conserved
+    # and the ranks still contract to the average
+    assert abs(out[0][3] - 1.5) < 0.2 and abs(out[1][3] - 1.5) < 0.2

@@ -292,3 +292,61 @@ def test_scale_kernel():
     torch.testing.assert_close(sh, x.bfloat16())
     C.scale_(x, s, True, None)
     torch.testing.assert_close(x, ref, rtol=1e-6, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- #
+# failure handling: soft heartbeat = counted + retried wait, hard heartbeat = sticky
+# status + a VALID parameter state
+# --------------------------------------------------------------------------- #
+def test_slow_peer_is_waited_for_counted_and_mass_is_conserved():
+    import time
+    n, numel = 2, 2 * CHUNK
+    engines, graphs, _, streams = _mk_world(n, numel, sgp.NPeerDynamicDirectedExponentialGraph, 1)
+    ogs, oms = _oracle_graphs(graphs)
+    C = engines[0].C
+    for e in engines:
+        e._state_i32[C.STATE_OFF_SOFT_TIMEOUT_US // 4] = 50_000        # 50 ms soft, 10 s hard
+        e.set_hyper(0.1, 0.9, 0.0, False)
+    zs = [e.z.double().clone() for e in engines]
+    gs = [e.grad.double().clone() for e in engines]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(streams[0]):
+        engines[0].mix(sgd=True)
+    time.sleep(0.4)                                  # rank 1 is 0.4 s late: past the soft heartbeat
+    with torch.cuda.stream(streams[1]):
+        engines[1].mix(sgd=True)
+    torch.cuda.synchronize()
+    for e in engines:
+        e.check()                                    # no hard failure
+    assert engines[0].soft_timeouts >= 1             # ... but the delay was noticed
+    engines[0].poll(blocking=True)
+    engines[0].poll(blocking=True)                   # (logs the retried wait; must not raise)
+    xs = []
+    for i in range(n):
+        x, _ = oracle.sgd_momentum(zs[i], gs[i], torch.zeros_like(zs[i]), 0.1, 0.9, 0.0, False)
+        xs.append(x)
+    xs, ws = oracle.mix_columns(xs, [1.0] * n, ogs, oms)
+    for i, e in enumerate(engines):
+        torch.testing.assert_close(e.z.double(), xs[i] / ws[i], rtol=1e-5, atol=1e-6)
+    assert abs(sum(e.ps_weight for e in engines) - n) < 1e-5          # push-sum mass conserved
+
+
+def test_dead_peer_trips_the_heartbeat_and_leaves_valid_parameters():
+    n, numel = 2, 2 * CHUNK
+    engines, graphs, _, streams = _mk_world(n, numel, sgp.NPeerDynamicDirectedExponentialGraph, 1)
+    e = engines[0]
+    e.ctx.set_timeout(0.3)
+    e.set_hyper(0.1, 0.0, 0.0, False)
+    z0, g0 = e.z.double().clone(), e.grad.double().clone()
+    with torch.cuda.stream(streams[0]):
+        e.mix(sgd=True)                              # rank 1 never launches
+    torch.cuda.synchronize()
+    with pytest.raises(NameError, match='Gossip flag timeout'):
+        e.poll(blocking=True)
+    with pytest.raises(RuntimeError):
+        e.check()
+    # every in-message was lost, nothing stale: z is the de-biased SGD result of this step
+    torch.testing.assert_close(e.z.double(), z0 - 0.1 * g0, rtol=1e-6, atol=1e-7)
+    assert e.device_step == 1
+    e.clear_status()
+    e.poll(blocking=True)                            # healthy again after the application cleared it
