@@ -184,6 +184,7 @@ def main(args):
         'SGP_REF_VISIBLE', str(local_rank))
     os.environ['SLURM_PROCID'] = str(rank)
     os.environ['SLURM_NTASKS'] = str(world)
+    os.environ['SLURM_LOCALID'] = '0'            # (gossip_sgd_adpsgd.py:627; one visible GPU per process)
     os.environ['HOSTNAME'] = os.environ.get('MASTER_ADDR', '127.0.0.1')
     master_port = os.environ.get('MASTER_PORT', '40100')
 

@@ -254,25 +254,52 @@ def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
     # what gossip costs per step after all overlap (kernel time + waiting for the in-neighbours)
     exposed = None
     if world > 1 and args.algo != 'ar' and not args.skip_local:
+        g_gossip = trainer.graph
         if args.algo == 'adpsgd':
-            model.disable_gossip()           # the captured graph is forward/backward only
+            g_local = g_gossip               # the captured graph is forward/backward only
+
+            def switch(gossip_on):
+                model.enable_gossip() if gossip_on else model.disable_gossip()
         else:
             model.gossip_enable = False
             trainer.graph = None
             trainer._eager_steps = 0
-        for i in range(5):
-            trainer.step(*pool[i % len(pool)])
-        sync_all()
-        e0.record(trainer.stream)
-        for i in range(K):
-            trainer.step_resident()
-        e1.record(trainer.stream)
-        sync_all()
-        ms3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-        local_ms = ms3.item() / K
-        exposed = {'ms_per_step': round(ms / K - local_ms, 4), 'local_only_ms_per_step': round(local_ms, 4),
-                   'how': 'same captured step with gossip disabled (SGD-only kernel), same GPUs, max over ranks'}
+            for i in range(5):               # eager warm-up + capture of the gossip-free step
+                trainer.step(*pool[i % len(pool)])
+            g_local = trainer.graph
+
+            def switch(gossip_on):
+                if not gossip_on and model.gossip_enable:
+                    trainer.finish()         # land the deferred SGD / gathered residual (overlap) first
+                model.gossip_enable = gossip_on
+                trainer.graph = g_gossip if gossip_on else g_local
+
+        def timed(gossip_on):
+            switch(gossip_on)
+            for i in range(2):
+                trainer.step_resident()
+            sync_all()
+            e0.record(trainer.stream)
+            for i in range(K):
+                trainer.step_resident()
+            e1.record(trainer.stream)
+            sync_all()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item() / K
+
+        # A B A B: alternate so that clock / thermal drift hits both arms alike
+        with_g, without = [], []
+        for _ in range(2):
+            without.append(timed(False))
+            with_g.append(timed(True))
+        g_ms, l_ms = sum(with_g) / 2, sum(without) / 2
+        exposed = {'ms_per_step': round(g_ms - l_ms, 4), 'with_gossip_ms_per_step': round(g_ms, 4),
+                   'local_only_ms_per_step': round(l_ms, 4),
+                   'runs_ms': {'with_gossip': [round(v, 4) for v in with_g], 'local_only': [round(v, 4) for v in without]},
+                   'how': 'same captured step with gossip switched off (SGD-only kernel; every rank trains '
+                          'alone), same GPUs, K steps each, alternated local/gossip/local/gossip, max over ranks'}
+        switch(True)
         trainer.finish()
     if args.algo == 'adpsgd':
         model.shutdown()

@@ -4,9 +4,10 @@
 // (VERDICT r1).  This allocator does what NVLS needs:
 //
 //   every rank   cuMemCreate (POSIX-fd exportable physical memory on its GPU), map it
-//   exchange     the fds travel as integers over the c10d control plane; a peer duplicates them
-//                out of the owner's process with pidfd_open + pidfd_getfd (no fabric / IMEX
-//                daemon, no unix-socket protocol) and cuMemImportFromShareableHandle's them
+//   exchange     the POSIX fds are passed between the ranks' processes over abstract unix-domain
+//                sockets (SCM_RIGHTS; `FdChannel` below -- pidfd_getfd is refused with EPERM inside
+//                the GPU containers, profiles/gputest_multigpu_n2_r2_nvls_attempt1.log), then
+//                cuMemImportFromShareableHandle'd; no fabric handles / IMEX daemon needed
 //   unicast      every peer's allocation is mapped (cuMemAddressReserve / cuMemMap / cuMemSetAccess):
 //                plain P2P loads / stores / cp.async.bulk over NVLink work as before
 //   multicast    symmetric rank 0 creates the multicast object (cuMulticastCreate), everyone adds
@@ -21,7 +22,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <sys/socket.h>
 #include <sys/syscall.h>
+#include <sys/un.h>
 #include <unistd.h>
 
 #include <cstring>
@@ -69,10 +72,12 @@ CUmemAllocationProp alloc_prop(int device)
     return p;
 }
 
-// duplicate file descriptor `fd` of process `pid` into this process
+// `fd` as usable in this process: a same-process handle is dup'ed; a foreign (pid, fd) pair is
+// first tried with pidfd_getfd (works on hosts that allow it); the portable path is FdChannel,
+// where the owner SENDS the descriptor and `fd` is already ours (pid == 0).
 int steal_fd(int pid, int fd)
 {
-    if (pid == (int)getpid()) return dup(fd);
+    if (pid == 0 || pid == (int)getpid()) return dup(fd);
     const int pidfd = (int)syscall(SYS_pidfd_open, pid, 0);
     if (pidfd < 0) throw std::runtime_error("pidfd_open failed (errno " + std::to_string(errno) + ")");
     const int got = (int)syscall(SYS_pidfd_getfd, pidfd, fd, 0);
@@ -81,6 +86,17 @@ int steal_fd(int pid, int fd)
     if (got < 0) throw std::runtime_error("pidfd_getfd failed (errno " + std::to_string(err) +
                                           "): cannot import the peer's memory handle");
     return got;
+}
+
+sockaddr_un abstract_addr(const std::string& name, socklen_t& len)
+{
+    sockaddr_un a;
+    std::memset(&a, 0, sizeof(a));
+    a.sun_family = AF_UNIX;
+    if (name.size() + 1 >= sizeof(a.sun_path)) throw std::runtime_error("socket name too long");
+    std::memcpy(a.sun_path + 1, name.data(), name.size());          // leading NUL: abstract namespace
+    len = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + name.size());
+    return a;
 }
 
 struct Mapping {                 // one mapped range; unmapped + released with the last tensor using it
@@ -270,8 +286,99 @@ private:
     std::shared_ptr<Mapping> local_map_, mc_map_;
 };
 
+// ---------------------------------------------------------------------------
+// FdChannel: pass file descriptors between the ranks of one host (SCM_RIGHTS over abstract
+// unix-domain sockets).  Every rank listens on "<job>.<rank>"; send() connects to the peer's name and
+// ships (sender rank, tag, fd); recv() accepts one connection.  Sends never block on the receiver
+// (the kernel queues the connection and the message), so "everybody sends, then everybody
+// receives" cannot deadlock.
+// ---------------------------------------------------------------------------
+class FdChannel {
+public:
+    FdChannel(const std::string& job, int rank, int world) : job_(job), rank_(rank)
+    {
+        sock_ = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (sock_ < 0) throw std::runtime_error("socket() failed");
+        socklen_t len;
+        sockaddr_un a = abstract_addr(job + "." + std::to_string(rank), len);
+        if (bind(sock_, reinterpret_cast<sockaddr*>(&a), len) != 0 || listen(sock_, world * 8 + 8) != 0) {
+            const int e = errno;
+            close(sock_);
+            throw std::runtime_error("bind/listen on the fd channel failed (errno " + std::to_string(e) + ")");
+        }
+    }
+    ~FdChannel() { if (sock_ >= 0) close(sock_); }
+
+    void send(int peer, int tag, int fd)
+    {
+        const int c = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (c < 0) throw std::runtime_error("socket() failed");
+        socklen_t len;
+        sockaddr_un a = abstract_addr(job_ + "." + std::to_string(peer), len);
+        int tries = 0;
+        while (connect(c, reinterpret_cast<sockaddr*>(&a), len) != 0) {
+            if (++tries > 2000) { close(c); throw std::runtime_error("fd channel: cannot reach rank " + std::to_string(peer)); }
+            usleep(5000);                    // the peer has not bound its socket yet
+        }
+        int payload[2] = {rank_, tag};
+        iovec iov = {payload, sizeof(payload)};
+        char ctrl[CMSG_SPACE(sizeof(int))];
+        std::memset(ctrl, 0, sizeof(ctrl));
+        msghdr msg;
+        std::memset(&msg, 0, sizeof(msg));
+        msg.msg_iov = &iov;
+        msg.msg_iovlen = 1;
+        msg.msg_control = ctrl;
+        msg.msg_controllen = sizeof(ctrl);
+        cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+        cm->cmsg_level = SOL_SOCKET;
+        cm->cmsg_type = SCM_RIGHTS;
+        cm->cmsg_len = CMSG_LEN(sizeof(int));
+        std::memcpy(CMSG_DATA(cm), &fd, sizeof(int));
+        const ssize_t n = sendmsg(c, &msg, 0);
+        const int e = errno;
+        close(c);
+        if (n != (ssize_t)sizeof(payload)) throw std::runtime_error("fd channel: sendmsg failed (errno " + std::to_string(e) + ")");
+    }
+
+    // -> (sender rank, tag, fd usable in this process)
+    py::tuple recv()
+    {
+        const int c = accept(sock_, nullptr, nullptr);
+        if (c < 0) throw std::runtime_error("fd channel: accept failed");
+        int payload[2] = {-1, -1};
+        iovec iov = {payload, sizeof(payload)};
+        char ctrl[CMSG_SPACE(sizeof(int))];
+        msghdr msg;
+        std::memset(&msg, 0, sizeof(msg));
+        msg.msg_iov = &iov;
+        msg.msg_iovlen = 1;
+        msg.msg_control = ctrl;
+        msg.msg_controllen = sizeof(ctrl);
+        const ssize_t n = recvmsg(c, &msg, MSG_WAITALL);
+        close(c);
+        int fd = -1;
+        for (cmsghdr* cm = CMSG_FIRSTHDR(&msg); cm != nullptr; cm = CMSG_NXTHDR(&msg, cm))
+            if (cm->cmsg_level == SOL_SOCKET && cm->cmsg_type == SCM_RIGHTS) std::memcpy(&fd, CMSG_DATA(cm), sizeof(int));
+        if (n != (ssize_t)sizeof(payload) || fd < 0) throw std::runtime_error("fd channel: no descriptor received");
+        return py::make_tuple(payload[0], payload[1], fd);
+    }
+
+private:
+    std::string job_;
+    int rank_;
+    int sock_ = -1;
+};
+
+static void close_fd(int fd) { if (fd >= 0) close(fd); }
+
 void bind_vmm(py::module& mod)
 {
+    py::class_<FdChannel, std::shared_ptr<FdChannel>>(mod, "FdChannel")
+        .def(py::init<const std::string&, int, int>(), py::arg("job"), py::arg("rank"), py::arg("world"))
+        .def("send", &FdChannel::send, py::call_guard<py::gil_scoped_release>())
+        .def("recv", &FdChannel::recv);
+    mod.def("close_fd", &close_fd);
     mod.def("vmm_caps", &vmm_caps, "multicast / handle-type capabilities of a device");
     mod.def("vmm_padded_size", &vmm_padded_size);
     py::class_<VmmBuffer, std::shared_ptr<VmmBuffer>>(mod, "VmmBuffer")

@@ -562,34 +562,10 @@ def make_bilat_trainer(model: BilatGossipDataParallel, lr, criterion=None, amp_d
             self.opt = _Opt()
             self.engine = _BilatEngineShim(model)
             self.k = None
-            from ..ops.fused_loss import FusedCrossEntropyWithAccuracy
-            self.criterion = criterion or FusedCrossEntropyWithAccuracy()
-            self._fused_loss = isinstance(self.criterion, FusedCrossEntropyWithAccuracy)
-            self.amp_dtype = amp_dtype
-            self.use_graph = use_cuda_graph
-            self.warmup_iters = warmup_iters
-            self.channels_last = channels_last
-            self.device = self.engine.device
             self.overlap = False
             self.gossip = False
-            self.graph = None
-            self.static_in = self.static_tgt = self.static_loss = self.static_out = None
-            self.static_metrics = None
-            self._eager_steps = 0
-            import os
-            self.batched_grad_copy = os.environ.get('SGP_B200_BATCHED_GRAD_COPY', '1') != '0'
-            self._grad_slots = None
-            self.stream = torch.cuda.Stream(device=self.device)
-            self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._stage = self._stage_tgt = None
-            self._stage_ready = torch.cuda.Event()
-            self._stage_free = torch.cuda.Event()
-            self._prefetched = False
-            self._loss_ring = None
-            self._loss_slot = 0
-            self._skip_next_sgd = False
-            self.own_launches_per_step = None
+            self._init_runtime(self.engine.device, criterion, amp_dtype, use_cuda_graph, warmup_iters,
+                               channels_last)
 
         def _one_step(self, first=False):
             self._fwd_bwd()                      # the captured part

@@ -295,6 +295,18 @@ class GossipDataParallel(Module):
             graph = NPDDEGraph(rank, world_size, self.nprocs_per_node, self.local_rank)
         if mixing is None:
             mixing = UniformMixing(graph, comm_device)
+        # push_sum=False is D-PSGD (the reference swaps in its PushPull gossiper,
+        # gossip/distributed.py:145-150).  Plain averaging is only correct when the mixing matrix
+        # is doubly stochastic -- on the circulant schedules of graph_manager that means every
+        # phase is balanced (as many in- as out-neighbours), and then the push-sum weight stays
+        # exactly 1.  Both data planes here always carry the weight (one scalar), so the flag
+        # selects no different code path; it is validated instead of silently ignored.
+        if not push_sum:
+            for outs, ins in graph.phases():
+                if len(outs) != len(ins):
+                    raise ValueError('push_sum=False (D-PSGD) needs a balanced schedule (doubly '
+                                     'stochastic mixing): phase with out-peers %s but in-peers %s'
+                                     % (sorted(outs), sorted(ins)))
 
         self.dist_config = {
             'verbose': verbose, 'comm_device': comm_device, 'graph': graph,

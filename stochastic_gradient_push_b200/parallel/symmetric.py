@@ -107,6 +107,36 @@ class VmmSymmetricWorld(SymmetricWorld):
         caps = native.load().vmm_caps(int(dev))
         return bool(caps.get('multicast') and caps.get('posix_fd'))
 
+    def _channel(self):
+        """lazily created fd-passing channel (abstract unix sockets named after a job token that
+        symmetric rank 0 draws and broadcasts over the control plane)"""
+        if getattr(self, '_fdx', None) is None:
+            import os
+            import uuid
+            tok = [None]
+            if self.rank == 0:
+                tok[0] = 'sgp_b200.%d.%s' % (os.getpid(), uuid.uuid4().hex[:12])
+            if self.world > 1:
+                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                dist.broadcast_object_list(tok, src=src, group=self.group)
+            self._fdx = self._C.FdChannel(tok[0], self.rank, self.world)
+            if self.world > 1:
+                dist.barrier(group=self.group)        # every rank listens before anybody connects
+        return self._fdx
+
+    def _exchange_fds(self, fd: int, tag: int):
+        """everybody sends `fd` to every peer, then receives world-1 descriptors -> {rank: fd}"""
+        ch = self._channel()
+        for r in range(self.world):
+            if r != self.rank:
+                ch.send(r, tag, int(fd))
+        got = {}
+        for _ in range(self.world - 1):
+            src, t, f = ch.recv()
+            assert t == tag, 'fd channel out of step (tag %d, expected %d)' % (t, tag)
+            got[int(src)] = int(f)
+        return got
+
     def alloc(self, name: str, nbytes: int, multicast: bool = True) -> _Buffer:
         assert name not in self.buffers
         C = self._C
@@ -114,28 +144,30 @@ class VmmSymmetricWorld(SymmetricWorld):
         vb = C.VmmBuffer(int(nbytes), self.device.index, self.world)
         buf.vmm = vb
         buf.local = vb.local()
-        gathered = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(gathered, (vb.pid(), vb.fd(), int(nbytes)), group=self.group)
+        self._tag = getattr(self, '_tag', 0) + 2
+        tag = self._tag
+        fds = self._exchange_fds(vb.fd(), tag) if self.world > 1 else {}
         buf.peers = []
         for r in range(self.world):
             if r == self.rank:
                 buf.peers.append(buf.local)
             else:
-                pid, fd, nb = gathered[r]
-                assert nb == nbytes, 'symmetric allocations must have equal size'
-                buf.peers.append(vb.open_peer(int(pid), int(fd)))
+                buf.peers.append(vb.open_peer(0, fds[r]))       # pid 0: the descriptor is already ours
+                C.close_fd(fds[r])
         buf.table = torch.tensor([t.data_ptr() for t in buf.peers], dtype=torch.int64, device=self.device)
         if self.world > 1:
-            dist.barrier(group=self.group)            # every fd has been duplicated by every peer
+            dist.barrier(group=self.group)
         if multicast and self.world > 1:
-            info = [None]
+            ch = self._channel()
             if self.rank == 0:
-                info[0] = (vb.pid(), vb.mc_create())
-            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
-            dist.broadcast_object_list(info, src=src, group=self.group)
-            if self.rank != 0:
-                vb.mc_import(int(info[0][0]), int(info[0][1]))
+                mc_fd = vb.mc_create()
+                for r in range(1, self.world):
+                    ch.send(r, tag + 1, int(mc_fd))
+            else:
+                src, t, f = ch.recv()
+                assert src == 0 and t == tag + 1
+                vb.mc_import(0, int(f))
+                C.close_fd(int(f))
             dist.barrier(group=self.group)
             vb.mc_add_device()
             dist.barrier(group=self.group)            # all devices joined before anybody binds

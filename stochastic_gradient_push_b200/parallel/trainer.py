@@ -44,6 +44,13 @@ class GossipTrainer(object):
         self.opt = optimizer
         self.engine = model._kernel.engine
         self.k = model._kernel
+        self.overlap = model.overlap
+        self.gossip = model.dist_config['world_size'] > 1
+        self._init_runtime(self.engine.device, criterion, amp_dtype, use_cuda_graph, warmup_iters,
+                           channels_last)
+
+    def _init_runtime(self, device, criterion, amp_dtype, use_cuda_graph, warmup_iters, channels_last):
+        """state shared by every trainer flavour (gossip / all-reduce / bilateral)"""
         # default: fused softmax cross-entropy that also yields prec@1 / prec@5 (the reference loop
         # measures both every iteration, gossip_sgd.py:394-399) in the same launch
         self.criterion = criterion or FusedCrossEntropyWithAccuracy()
@@ -52,9 +59,7 @@ class GossipTrainer(object):
         self.use_graph = use_cuda_graph
         self.warmup_iters = warmup_iters
         self.channels_last = channels_last
-        self.device = self.engine.device
-        self.overlap = model.overlap
-        self.gossip = model.dist_config['world_size'] > 1
+        self.device = device
         self.graph = None
         self.static_in = None
         self.static_tgt = None

@@ -124,13 +124,13 @@ def test_single_process_multi_replica_mode_matches_one_big_batch(fused):
         y = torch.randn(24, 4, device=dev, generator=g)
         out = model(x)
         assert out.shape == (24, 4) and out.device == dev
-        ((out - y) ** 2).sum().backward()
+        (((out - y) ** 2).sum() / x.shape[0]).backward()      # (a stable step size: sum / batch)
         opt.step()
         opt.zero_grad(set_to_none=False) if not fused else opt.zero_grad()
         model.transfer_params()
         model._query_gossip_queue()
         model._flush_pending()
-        ((ref(x) - y) ** 2).sum().backward()
+        (((ref(x) - y) ** 2).sum() / x.shape[0]).backward()
         ropt.step()
         ropt.zero_grad()
     torch.cuda.synchronize()
