@@ -88,6 +88,11 @@ def main_adpsgd(args, rank, world, master_port, torch, dist):
     if not os.path.isfile(script):
         unavailable('baseline/_ref/bin/gossip_sgd_adpsgd.py missing (cp from the reference tree)')
     mp.set_start_method('forkserver', force=True)
+    # two worlds, both hosted by THEIR rank 0 (training world on port+1, gossip world on port): the
+    # launcher's agent store only serves the launcher's own port, so the scripts must create their
+    # TCP stores themselves on a port pair next to it
+    os.environ.pop('TORCHELASTIC_USE_AGENT_STORE', None)
+    master_port = str(int(master_port) + 17)
     spec = importlib.util.spec_from_file_location('ref_gossip_sgd_adpsgd', script)
     ref = importlib.util.module_from_spec(spec)
     ckpt = tempfile.mkdtemp(prefix='ref_ckpt_') + '/'

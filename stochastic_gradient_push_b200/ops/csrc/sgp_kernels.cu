@@ -559,13 +559,10 @@ sgp_gather_tma_kernel(const SgpArgs a, const int pub_grid)
 // and an NVLink-bound phase 2 (0.257 ms at ResNet-50 size on 2 GPUs = 52 % of the NVLink
 // roofline, profiles/README.md).  Here the two phases run on different warps of the same CTA:
 //
-//   warps 0-3 (group A)    phase 1, segment by segment: SGD-momentum + publish (HBM stream); after
-//                          each segment: release the per-CTA flag to the peers, arrive on a local
-//                          mbarrier for group B
-//   warps 4-7 (group B)    phase 2 of the segments group A has finished: own term from L2, the
-//                          peers' data from SHARED MEMORY (landed by TMA), de-bias, store -- runs
-//                          concurrently with group A, so the HBM stream of phase 1 and the NVLink
-//                          stream of phase 2 overlap inside every CTA
+//   warps 0-7 (consumers)  for seg = 0..K:   phase 1 of segment `seg`   (SGD + publish, HBM)
+//                                            phase 2 of segment `seg-1` (mix + de-bias)
+//                          phase 2 reads the peers' data from SHARED MEMORY, where it has
+//                          been landing while phase 1 of the next segment was streaming HBM
 //   warp 8 lane 0 (producer) per segment: acquire the in-neighbours' publish flags, then keep
 //                          a ring of PIPE_STAGES x 16 KB bulk copies (cp.async.bulk,
 //                          peer global -> shared, mbarrier complete_tx) in flight over NVLink
@@ -576,16 +573,19 @@ sgp_gather_tma_kernel(const SgpArgs a, const int pub_grid)
 // sgp_step_kernel (gather / probe / the old kernel interoperate with it); the grid must be
 // the same on all ranks (flags are matched by CTA index).
 //
+// (Tried and rejected, round 2: splitting the consumers into a phase-1 group and a phase-2 group of
+// four warps each so that both streams run concurrently inside a CTA -- 0.298 ms vs 0.254 ms for
+// this version on 2 GPUs: four warps per stream no longer cover the HBM / shared-memory latencies.)
+//
 // A timed-out flag wait does not leave stale parameters behind: the producer marks the CTA
 // failed, completes its barriers without data, and the consumers de-bias their own published
 // numerator instead (z = x_own / w1, i.e. "every in-message of this round was lost" -- a valid
 // push-sum state); the sticky status word makes the host raise at its next poll.
 // ---------------------------------------------------------------------------
 #define PIPE_STAGES    4
-#define PIPE_CONSUMERS SGP_THREADS                 // 256 = group A + group B
-#define PIPE_GROUP     (PIPE_CONSUMERS / 2)        // 128 threads per group
+#define PIPE_CONSUMERS SGP_THREADS                 // 256: the chunk decomposition of sgp_step_kernel
 #define PIPE_THREADS   (PIPE_CONSUMERS + 32)
-#define PIPE_SMEM      (PIPE_STAGES * SGP_TMA_BYTES + (2 * PIPE_STAGES + 1 + SGP_SEQ_STRIDE) * 8 + 64)
+#define PIPE_SMEM      (PIPE_STAGES * SGP_TMA_BYTES + 2 * PIPE_STAGES * 8 + 64)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -603,8 +603,8 @@ sgp_step_pipe_kernel(const SgpArgs a)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + PIPE_STAGES * SGP_TMA_BYTES);
     uint64_t* empty = full + PIPE_STAGES;
     uint64_t* wbar = empty + PIPE_STAGES;            // new push-sum weight is known
-    uint64_t* segbar = wbar + 1;                     // [SGP_SEQ_STRIDE] group A finished segment s
     __shared__ float s_wn;
+    __shared__ int   s_ok;                            // WAR fence outcome (consumers)
     __shared__ volatile int s_fail;                   // producer: an in-neighbour timed out
 
     SgpState* st = a.st;
@@ -640,11 +640,11 @@ sgp_step_pipe_kernel(const SgpArgs a)
         if (k < row.n_in && row.in[k] >= 0) { in_rank[n_in] = row.in[k]; in_w[n_in] = row.in_w[k]; ++n_in; }
 
     if (tid == 0) {
-        for (int i = 0; i < PIPE_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PIPE_GROUP / 32); }
+        for (int i = 0; i < PIPE_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PIPE_CONSUMERS / 32); }
         mbar_init(wbar, 1);
-        for (int i = 0; i < SGP_SEQ_STRIDE; ++i) mbar_init(&segbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_fail = 0;
+        s_ok = 1;
     }
     __syncthreads();
 
@@ -686,38 +686,46 @@ sgp_step_pipe_kernel(const SgpArgs a)
             }
         }
         __syncwarp();
-    } else if (warp < PIPE_GROUP / 32) {
-        // ============================ group A: phase 1 (HBM stream) ============================
+    } else {
+        // ============================ consumers ============================
         const SgpHyper hp = *a.hyper;
         const uint64_t pol_first = l2_evict_first_policy();
         const uint64_t pol_last = l2_evict_last_policy();
         const bool do_sgd = (flags & SGP_F_SGD) && (hp.do_sgd != 0.f);
+        const int lane = tid & 31;
 
         if (step >= st->ack_from + 2u) {
             // WAR fence: outbox[parity] was last read at step-2 by that step's out-neighbours
             if (tid == 0) {
                 RowInfo prev;
                 load_row(a, step - 2u, prev);
+                int ok = 1;
                 for (int k = 0; k < prev.n_out; ++k) {
                     const int o = prev.out[k];
                     if (o == a.rank || o < 0) continue;
-                    spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_ACK);
+                    ok &= spin_wait_geq(&mypad->ack_seq[o], step - 1u, st, a.timeout_ns, SGP_ERR_TIMEOUT_ACK) ? 1 : 0;
                 }
+                s_ok = ok;
             }
-            asm volatile("bar.sync 1, %0;" :: "n"(PIPE_GROUP) : "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"(PIPE_CONSUMERS) : "memory");
         }
 
-        for (int seg = 0; seg < K; ++seg) {
-            const long long it_lo = my_chunks * seg / K, it_hi = my_chunks * (seg + 1) / K;
-            for (long long it = it_lo; it < it_hi; ++it) {
-                const long long c = b + it * gridDim.x;
-#pragma unroll 1
-                for (int h = 0; h < SGP_THREADS / PIPE_GROUP; ++h) {      // the group covers a chunk in 2 sweeps
-                    const long long base = c * SGP_CHUNK + ((long long)h * SGP_UNROLL * PIPE_GROUP + tid) * SGP_VEC;
+        int cstage = 0;
+        uint32_t cphase = 0;
+        float inv_wn = 1.f;
+        const float inv_w1 = 1.f / w1;
+
+        for (int seg = 0; seg <= K; ++seg) {
+            // ---------------- phase 1 of segment `seg`: local update + publish ----------------
+            if (seg < K) {
+                const long long it_lo = my_chunks * seg / K, it_hi = my_chunks * (seg + 1) / K;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
                     float4 x[SGP_UNROLL], g[SGP_UNROLL], m[SGP_UNROLL];
 #pragma unroll
                     for (int u = 0; u < SGP_UNROLL; ++u) {
-                        const long long i = base + (long long)u * PIPE_GROUP * SGP_VEC;
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
                         x[u] = ld_once_f4(reinterpret_cast<const float4*>(a.z + i), pol_first);
                         if (do_sgd) {
                             if (flags & SGP_F_GRAD_BF16)
@@ -727,15 +735,15 @@ sgp_step_pipe_kernel(const SgpArgs a)
                                 g[u] = ld_once_f4(reinterpret_cast<const float4*>(
                                            reinterpret_cast<const float*>(a.g) + i), pol_first);
                             if (a.g2 != nullptr) {
-                                const float4 hh = ld_once_f4(reinterpret_cast<const float4*>(a.g2 + i), pol_first);
-                                g[u].x += hh.x; g[u].y += hh.y; g[u].z += hh.z; g[u].w += hh.w;
+                                const float4 h = ld_once_f4(reinterpret_cast<const float4*>(a.g2 + i), pol_first);
+                                g[u].x += h.x; g[u].y += h.y; g[u].z += h.z; g[u].w += h.w;
                             }
                             m[u] = ld_once_f4(reinterpret_cast<const float4*>(a.m + i), pol_first);
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < SGP_UNROLL; ++u) {
-                        const long long i = base + (long long)u * PIPE_GROUP * SGP_VEC;
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
                         float4 xv = mul4(x[u], wmul);
                         if (do_sgd) {
                             float4 gv = mul4(g[u], hp.grad_scale);
@@ -759,61 +767,52 @@ sgp_step_pipe_kernel(const SgpArgs a)
                         st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
                     }
                 }
-            }
-            asm volatile("bar.sync 1, %0;" :: "n"(PIPE_GROUP) : "memory");
-            if (tid == 0) {
-                if (seg == 0) st_relaxed_sys_f32(&mypad->psw[parity], w1);
-                __threadfence_system();
-                st_release_sys(&mypad->pub_seq[b], seq_base + (uint32_t)seg + 1u);     // to the peers
-                mbar_arrive(&segbar[seg]);                                           // to group B
-            }
-        }
-    } else {
-        // ============================ group B: phase 2 (mix + de-bias) ============================
-        const uint64_t pol_first = l2_evict_first_policy();
-        const int t = tid - PIPE_GROUP;                    // 0..127
-        const int lane = tid & 31;
-        constexpr int PER = SGP_CHUNK / SGP_VEC / PIPE_GROUP;      // 8 float4 per thread and chunk
-        int cstage = 0;
-        uint32_t cphase = 0;
-        float inv_wn = 1.f;
-        const float inv_w1 = 1.f / w1;
-        for (int seg = 0; seg < K; ++seg) {
-            mbar_wait(&segbar[seg], 0);                    // this CTA's outbox share of `seg` is written
-            if (seg == 0) {
-                mbar_wait(wbar, 0);
-                inv_wn = 1.f / s_wn;
-            }
-            const long long it_lo = my_chunks * seg / K, it_hi = my_chunks * (seg + 1) / K;
-            for (long long it = it_lo; it < it_hi; ++it) {
-                const long long c = b + it * gridDim.x;
-                const long long base = c * SGP_CHUNK + (long long)t * SGP_VEC;
-                float4 acc[PER];
-#pragma unroll
-                for (int j = 0; j < PER; ++j)
-                    acc[j] = mul4(ld_once_f4(reinterpret_cast<const float4*>(
-                                      my_out + base + (long long)j * PIPE_GROUP * SGP_VEC), pol_first),   // L2 hit
-                                  row.self_w);
-                for (int k = 0; k < n_in; ++k) {
-                    mbar_wait(&full[cstage], cphase);
-                    const float4* src = reinterpret_cast<const float4*>(ring + (size_t)cstage * SGP_CHUNK);
-                    const float wk = in_w[k];
-#pragma unroll
-                    for (int j = 0; j < PER; ++j) acc[j] = fma4(src[t + j * PIPE_GROUP], wk, acc[j]);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[cstage]);     // this warp is done with the stage
-                    if (++cstage == PIPE_STAGES) { cstage = 0; cphase ^= 1u; }
+                asm volatile("bar.sync 1, %0;" :: "n"(PIPE_CONSUMERS) : "memory");
+                if (tid == 0) {
+                    if (seg == 0) st_relaxed_sys_f32(&mypad->psw[parity], w1);
+                    __threadfence_system();
+                    st_release_sys(&mypad->pub_seq[b], seq_base + (uint32_t)seg + 1u);
                 }
-                const bool failed = s_fail != 0;           // (rare: re-read the own numerator)
+            }
+            // ---------------- phase 2 of segment `seg - 1`: mix + de-bias ----------------
+            if (seg >= 1) {
+                const int ps = seg - 1;
+                if (ps == 0) {
+                    mbar_wait(wbar, 0);
+                    inv_wn = 1.f / s_wn;
+                }
+                const long long it_lo = my_chunks * ps / K, it_hi = my_chunks * (ps + 1) / K;
+                for (long long it = it_lo; it < it_hi; ++it) {
+                    const long long c = b + it * gridDim.x;
+                    const long long base = c * SGP_CHUNK + (long long)tid * SGP_VEC;
+                    float4 acc[SGP_UNROLL];
 #pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const long long i = base + (long long)j * PIPE_GROUP * SGP_VEC;
-                    const float4 zv = failed
-                        ? mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first), inv_w1)
-                        : mul4(acc[j], inv_wn);
-                    st_f4(reinterpret_cast<float4*>(a.z + i), zv);
-                    if (flags & SGP_F_SHADOW)
-                        st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        acc[u] = mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first),   // L2 hit
+                                      row.self_w);
+                    }
+                    for (int k = 0; k < n_in; ++k) {
+                        mbar_wait(&full[cstage], cphase);
+                        const float4* src = reinterpret_cast<const float4*>(ring + (size_t)cstage * SGP_CHUNK);
+                        const float wk = in_w[k];
+#pragma unroll
+                        for (int u = 0; u < SGP_UNROLL; ++u) acc[u] = fma4(src[tid + u * SGP_THREADS], wk, acc[u]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[cstage]);     // this warp is done with the stage
+                        if (++cstage == PIPE_STAGES) { cstage = 0; cphase ^= 1u; }
+                    }
+                    const bool failed = s_fail != 0;           // (rare: re-read the own numerator)
+#pragma unroll
+                    for (int u = 0; u < SGP_UNROLL; ++u) {
+                        const long long i = base + (long long)u * SGP_THREADS * SGP_VEC;
+                        const float4 zv = failed
+                            ? mul4(ld_once_f4(reinterpret_cast<const float4*>(my_out + i), pol_first), inv_w1)
+                            : mul4(acc[u], inv_wn);
+                        st_f4(reinterpret_cast<float4*>(a.z + i), zv);
+                        if (flags & SGP_F_SHADOW)
+                            st_u2(reinterpret_cast<uint2*>(a.shadow + i), f4_to_bf16x4(zv));
+                    }
                 }
             }
         }

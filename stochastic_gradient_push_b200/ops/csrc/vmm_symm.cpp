@@ -116,8 +116,14 @@ struct Mapping {                 // one mapped range; unmapped + released with t
 
 torch::Tensor tensor_over(std::shared_ptr<Mapping> m, size_t nbytes, int device)
 {
+    // target_device: the mapping may point at a PEER's physical memory (or at a multicast object);
+    // without it from_blob asks the driver where the memory lives and refuses "cuda:1 != cuda:0"
     auto opts = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, device);
-    return torch::from_blob(reinterpret_cast<void*>(m->va), {(int64_t)nbytes}, [m](void*) mutable { m.reset(); }, opts);
+    return torch::for_blob(reinterpret_cast<void*>(m->va), {(int64_t)nbytes})
+        .deleter([m](void*) mutable { m.reset(); })
+        .options(opts)
+        .target_device(c10::Device(c10::kCUDA, (c10::DeviceIndex)device))
+        .make_tensor();
 }
 
 std::shared_ptr<Mapping> map_handle(CUmemGenericAllocationHandle h, size_t size, size_t align, int device, bool own)

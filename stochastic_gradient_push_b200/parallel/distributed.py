@@ -75,7 +75,7 @@ class _KernelBackend(object):
             self.shadow.copy_(arena.flat)
         self.engine = GossipEngine(world_view, arena.flat, graph, mixing, shadow=self.shadow,
                                    with_residual=True, timeout_s=timeout_s, grid=grid,
-                                   name='gdp%d' % owner._instance_id)
+                                   name=owner._symm_name)
         self.gather_event = None
         self.residual_pending = False       # a gather finished/launched and is not folded yet
         self.sgd_pending = False            # FusedGossipSGD.step() deferred into next launch
@@ -238,11 +238,15 @@ class GossipDataParallel(Module):
                  overlap=False, synch_freq=0, verbose=False, use_streams=True,
                  nprocs_per_node=1, local_node_group=None,
                  transport='auto', compute_dtype=None, symmetric_world=None,
-                 heartbeat_timeout=HEARTBEAT_TIMEOUT, grid=None):
+                 heartbeat_timeout=HEARTBEAT_TIMEOUT, grid=None, symmetric_name=None):
         super(GossipDataParallel, self).__init__()
         _INSTANCES[0] += 1
         self._instance_id = _INSTANCES[0]
         self._timeout_s = float(heartbeat_timeout)
+        # name of this wrapper's symmetric allocations: identical on every rank of the world
+        # (one instance per process: the instance counter; several virtual ranks inside ONE process
+        # -- LocalWorld loop-back -- must pass the same explicit name)
+        self._symm_name = symmetric_name or ('gdp%d' % self._instance_id)
         self.exposed_comm_s = 0.0       # c10d data plane: host seconds blocked waiting for peers
         self.gossip_retries = 0         # interrupted gossip rounds that were re-queued (soft retry)
 
@@ -501,7 +505,7 @@ class GossipDataParallel(Module):
             if self.asynch:
                 self._drain_async()
             self._query_gossip_queue()
-            self._flush_pending()
+            self._flush_pending(drain=True)
         super_dict = super(GossipDataParallel, self).state_dict(*args, **kwargs)
         return {'state_dict': super_dict,
                 'ps_weight': self.ps_weight.detach().cpu().clone(),
@@ -715,7 +719,7 @@ class GossipDataParallel(Module):
         # drain BEFORE disabling (the reference disables first, which turns its
         # own drain into a no-op) so no peer message is lost
         self._query_gossip_queue(non_blocking=self.asynch)
-        self._flush_pending()
+        self._flush_pending(drain=True)
         self.gossip_enable = False
         for module in self._module_copies[1:]:
             module.eval()
@@ -730,7 +734,7 @@ class GossipDataParallel(Module):
         if self.asynch:
             self._drain_async()
         self._query_gossip_queue(non_blocking=False)
-        self._flush_pending()
+        self._flush_pending(drain=True)
 
     def _drain_async(self):
         """Collective drain for bounded-staleness runs, where ranks start different
@@ -870,9 +874,11 @@ class GossipDataParallel(Module):
             return True
         return False
 
-    def _flush_pending(self):
+    def _flush_pending(self, drain=False):
         """Apply a deferred fused-SGD step and/or fold a gathered residual
-        without starting a new gossip (eval / checkpoint / sync_comms)."""
+        without starting a new gossip (eval / checkpoint / sync_comms).  ``drain=True`` (the
+        explicit drain points) also synchronises and raises on a reported heartbeat failure; the
+        per-iteration call from the forward pre-hook only does the non-blocking poll."""
         k = self._kernel
         if k is None:
             return
@@ -881,8 +887,7 @@ class GossipDataParallel(Module):
                            in_numerator=self.is_ps_numerator)
             k.residual_pending = False
             self.is_ps_numerator = False
-        # drain points (state_dict / sync_comms / eval / schedule change): a blocking health check
-        k.engine.poll(blocking=True)
+        k.engine.poll(blocking=drain)
 
     # -- hooks ----------------------------------------------------------------- #
     def __register_hooks(self):

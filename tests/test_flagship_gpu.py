@@ -140,6 +140,27 @@ def test_single_process_multi_replica_mode_matches_one_big_batch(fused):
     assert model._replica_arenas[1][0].flat.device.index == ids[1]
 
 
+def _train_tiny(compute_dtype, amp, steps=6, graph=False):
+    import stochastic_gradient_push_b200 as sgp
+    from stochastic_gradient_push_b200 import models
+    from stochastic_gradient_push_b200.optim import FusedGossipSGD
+    from stochastic_gradient_push_b200.parallel.distributed import GossipDataParallel
+    from stochastic_gradient_push_b200.parallel.trainer import GossipTrainer
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(3)
+    net = models.TinyConvNet(width=32).to(dev).to(memory_format=torch.channels_last)
+    model = GossipDataParallel(net, graph=sgp.NPeerDynamicDirectedExponentialGraph(0, 1), rank=0,
+                               world_size=1, heartbeat_timeout=20, compute_dtype=compute_dtype)
+    opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    tr = GossipTrainer(model, opt, amp_dtype=amp, use_cuda_graph=graph, warmup_iters=2)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(32, 3, 32, 32, generator=g).pin_memory()
+    y = torch.randint(0, 10, (32,), generator=g).pin_memory()
+    slots = [tr.step(x, y) for _ in range(steps)]
+    tr.finish()
+    return model, [float(tr.loss_ring[s]) for s in slots]
+
+
 @pytest.mark.parametrize('graph', [False, True])
 def test_bf16_shadow_twin_tracks_the_autocast_path(graph):
     m_twin, l_twin = _train_tiny(torch.bfloat16, torch.bfloat16, graph=graph)

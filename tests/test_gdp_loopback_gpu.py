@@ -25,7 +25,7 @@ def _world(n, graph_name, ppi, overlap, fused, nesterov):
         net = sim._model(r).to(dev)
         model = GossipDataParallel(net, graph=graph, overlap=overlap, rank=r, world_size=n,
                                    heartbeat_timeout=20, symmetric_world=lw.view(r), transport='nvlink',
-                                   grid=4)
+                                   grid=4, symmetric_name='loopback')
         assert model.transport == 'nvlink'
         if fused:
             opt = FusedGossipSGD(model, lr=sim.LR, momentum=sim.MU, weight_decay=sim.WD, nesterov=nesterov)
@@ -116,7 +116,7 @@ def test_loopback_graphed_trainer_equals_eager(algo):
             net = models.TinyConvNet().to(dev).to(memory_format=torch.channels_last)
             model = GossipDataParallel(net, graph=sgp.NPeerDynamicDirectedExponentialGraph(r, n),
                                        overlap=(algo == 'osgp'), rank=r, world_size=n, heartbeat_timeout=20,
-                                       symmetric_world=lw.view(r), transport='nvlink', grid=4)
+                                       symmetric_world=lw.view(r), transport='nvlink', grid=4, symmetric_name='loopback')
             opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
             trainers.append(GossipTrainer(model, opt, amp_dtype=None, use_cuda_graph=use_graph, warmup_iters=10 ** 6))
         gens = [torch.Generator().manual_seed(100 + r) for r in range(n)]
