@@ -289,6 +289,20 @@ public:
             SGP_CUDA_CHECK(sgp_launch_gather(&a, grid, pub_grid, at::cuda::getCurrentCUDAStream()));
     }
 
+    // Overlap-SGP gather on the copy engines: flag wait (1 CTA) -> cudaMemcpyAsync(peer outbox ->
+    // residual) -> ack (1 thread).  `src_ptr`: address of the in-neighbour's outbox half of this step.
+    void gather_dma(int pub_grid, int64_t src_ptr)
+    {
+        SgpArgs a = prepare(0);
+        TORCH_CHECK(a.residual && a.outboxes && src_ptr != 0);
+        c10::cuda::CUDAGuard guard(device_);
+        auto st = at::cuda::getCurrentCUDAStream();
+        SGP_CUDA_CHECK(sgp_launch_gather_wait(&a, pub_grid, st));
+        SGP_CUDA_CHECK(cudaMemcpyAsync(a.residual, reinterpret_cast<const void*>(src_ptr),
+                                       (size_t)a.n * sizeof(float), cudaMemcpyDefault, st));
+        SGP_CUDA_CHECK(sgp_launch_gather_ack(&a, st));
+    }
+
     void probe(int pub_grid, c10::optional<torch::Tensor> host_flag)
     {
         SgpArgs a = prepare(0);
@@ -650,6 +664,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("last_status", &BilatDaemon::last_status)
         .def("error", &BilatDaemon::error);
 
+    mod.attr("STATE_OFF_RES_SCALE") = (int)offsetof(SgpState, res_scale);
     mod.attr("STATE_OFF_SOFT_TIMEOUT_US") = (int)offsetof(SgpState, soft_timeout_us);
     mod.attr("STATE_OFF_SOFT_TIMEOUTS") = (int)offsetof(SgpState, soft_timeouts);
     mod.attr("STATE_OFF_BILAT_ROUND") = (int)offsetof(SgpState, bilat_round);
@@ -682,6 +697,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
         .def("max_grid", &GossipContext::max_grid)
         .def("step", &GossipContext::step, py::arg("flags"), py::arg("grid"))
         .def("gather", &GossipContext::gather, py::arg("grid"), py::arg("pub_grid"), py::arg("tma") = false)
+        .def("gather_dma", &GossipContext::gather_dma, py::arg("pub_grid"), py::arg("src_ptr"))
         .def("probe", &GossipContext::probe, py::arg("pub_grid"), py::arg("host_flag") = py::none())
         .def("allreduce_sgd", &GossipContext::allreduce_sgd)
         .def("barrier", &GossipContext::barrier);

@@ -72,7 +72,11 @@ struct __align__(128) SgpState {
     // analogue of the reference re-queueing an interrupted round (gossip/distributed.py:358-364)
     uint32_t soft_timeout_us;  // 0 = off
     uint32_t soft_timeouts;    // waits that went past the soft deadline (monotonic)
-    uint32_t _pad[15];
+    // overlap: factor the pending residual is multiplied with when it is folded.  1 when a gather
+    // KERNEL produced it (already weighted); the in-neighbour's edge weight when the residual is
+    // the raw outbox copied by the DMA engines (sgp_gather_wait / cudaMemcpyAsync / sgp_gather_ack)
+    float    res_scale;
+    uint32_t _pad[14];
 };
 
 // ---- hyper-parameters (device resident so CUDA graphs can retarget them) ----
@@ -259,6 +263,8 @@ cudaError_t sgp_launch_gather(const SgpArgs* args, int grid, int pub_grid, cudaS
 cudaError_t sgp_launch_gather_tma(const SgpArgs* args, int grid, int pub_grid, cudaStream_t stream);
 cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_flag,
                              cudaStream_t stream);
+cudaError_t sgp_launch_gather_wait(const SgpArgs* args, int pub_grid, cudaStream_t stream);
+cudaError_t sgp_launch_gather_ack(const SgpArgs* args, cudaStream_t stream);
 cudaError_t sgp_launch_bilat_decide(const SgpArgs* args, int pub_grid, int passive,
                                     unsigned long long max_wait_ns, uint32_t* host_fb, cudaStream_t stream);
 cudaError_t sgp_launch_bilat_ctl(SgpState* st, int budget, int enabled, cudaStream_t stream);

@@ -100,6 +100,7 @@ sgp_step_kernel(const SgpArgs a)
     const float w0 = *((volatile float*)&st->ps_weight[parity]);
     const float wmul = (flags & SGP_F_IN_NUMER) ? 1.f : w0;   // z -> numerator factor
     const float wres = (flags & SGP_F_FOLD_RES) ? *((volatile float*)&st->res_weight) : 0.f;
+    const float rscale = (flags & SGP_F_FOLD_RES) ? *((volatile float*)&st->res_scale) : 1.f;
     const float w1 = w0 + wres;                    // weight of the published numerator
 
     SgpSignalPad* mypad = a.pads[a.rank];
@@ -207,8 +208,9 @@ sgp_step_kernel(const SgpArgs a)
                                 st_f4(reinterpret_cast<float4*>(a.g2 + i), make_float4(0.f, 0.f, 0.f, 0.f));
                         }
                     }
-                    if (flags & SGP_F_FOLD_RES) {
-                        xv.x += r[u].x; xv.y += r[u].y; xv.z += r[u].z; xv.w += r[u].w;
+                    if (flags & SGP_F_FOLD_RES) {      // (rscale: 1 after a gather kernel, the edge weight after a DMA gather)
+                        xv.x = fmaf(r[u].x, rscale, xv.x); xv.y = fmaf(r[u].y, rscale, xv.y);
+                        xv.z = fmaf(r[u].z, rscale, xv.z); xv.w = fmaf(r[u].w, rscale, xv.w);
                     }
                     if (flags & SGP_F_PUBLISH)   // keep the outbox in L2 for phase 2 / peers
                         st_hint_f4(reinterpret_cast<float4*>(my_out + i), xv, pol_last);
@@ -413,6 +415,7 @@ sgp_gather_kernel(const SgpArgs a, const int pub_grid)
             if (j != a.rank) st_release_sys(&a.pads[j]->ack_seq[a.rank], s + 1u);
         }
         *((volatile float*)&st->res_weight) = s_ok ? wr : 0.f;
+        *((volatile float*)&st->res_scale) = 1.f;
         *((volatile uint32_t*)&st->done_ctas) = 0u;
         __threadfence();
     }
@@ -546,6 +549,7 @@ sgp_gather_tma_kernel(const SgpArgs a, const int pub_grid)
             if (j != a.rank) st_release_sys(&a.pads[j]->ack_seq[a.rank], s + 1u);
         }
         *((volatile float*)&st->res_weight) = s_ok ? wr : 0.f;
+        *((volatile float*)&st->res_scale) = 1.f;
         *((volatile uint32_t*)&st->done_ctas) = 0u;
         __threadfence();
     }
@@ -876,6 +880,57 @@ __global__ void sgp_probe_kernel(const SgpArgs a, const int pub_grid, uint32_t* 
 }
 
 // ---------------------------------------------------------------------------
+// Overlap-SGP gather on the COPY ENGINES (one in-neighbour per step).  A gather kernel on the side
+// stream -- even the 32-CTA TMA one -- holds SMs while the forward pass starts: persistent
+// one-CTA-per-SM kernels (the tcgen05 GEMMs) and 2-CTA/SM tile loops then wait for "their" SM, and
+// the overlap costs more than it hides (bench: OSGP +0.41 ms vs SGP +0.22 ms per step at 2 GPUs,
+// profiles/bench_r2_n2_*).  With a single in-neighbour the residual is just a copy of the peer's
+// outbox, so:
+//     sgp_gather_wait_kernel   ONE CTA: wait for the in-neighbour's publish flags of this step
+//     cudaMemcpyAsync          peer outbox -> residual, 100 MB over NVLink on a DMA engine: zero SMs
+//     sgp_gather_ack_kernel    ONE thread: residual weight / scale (= the edge weight; applied when
+//                              the next publish folds the residual), ack the outbox to its owner
+// ---------------------------------------------------------------------------
+__global__ void sgp_gather_wait_kernel(const SgpArgs a, const int pub_grid)
+{
+    SgpState* st = a.st;
+    const uint32_t s = *((volatile uint32_t*)&st->step) - 1u;
+    RowInfo row;
+    load_row(a, s, row);
+    int segs = a.segments < 1 ? 1 : a.segments;
+    if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
+    for (int k = 0; k < row.n_in; ++k) {
+        const int j = row.in[k];
+        if (j < 0) continue;
+        for (int f = threadIdx.x; f < pub_grid; f += blockDim.x)
+            spin_wait_geq(&a.pads[j]->pub_seq[f], s * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs, st,
+                          a.timeout_ns, SGP_ERR_TIMEOUT_PUB);
+    }
+}
+
+__global__ void sgp_gather_ack_kernel(const SgpArgs a)
+{
+    SgpState* st = a.st;
+    const uint32_t s = *((volatile uint32_t*)&st->step) - 1u;
+    const uint32_t parity = s & 1u;
+    RowInfo row;
+    load_row(a, s, row);
+    const bool ok = *((volatile uint32_t*)&st->status) == SGP_OK;
+    float wr = 0.f, scale = 0.f;
+    __threadfence_system();                         // the DMA copy before this kernel has completed
+    for (int k = 0; k < row.n_in; ++k) {
+        const int j = row.in[k];
+        if (j < 0) continue;
+        scale = row.in_w[k];                        // (single in-neighbour: enforced by the host)
+        wr = fmaf(row.in_w[k], ld_relaxed_sys_f32(&a.pads[j]->psw[parity]), wr);
+        if (j != a.rank) st_release_sys(&a.pads[j]->ack_seq[a.rank], s + 1u);
+    }
+    *((volatile float*)&st->res_weight) = ok ? wr : 0.f;
+    *((volatile float*)&st->res_scale) = ok ? scale : 0.f;
+    __threadfence();
+}
+
+// ---------------------------------------------------------------------------
 // AD-PSGD round state machine, device side.  One CTA decides what the NEXT worker launch
 // (sgp_step_kernel with SGP_F_FROM_STATE) does, from flags only:
 //   * active ranks publish their snapshot unconditionally, passive ranks only once their
@@ -1193,6 +1248,18 @@ cudaError_t sgp_launch_probe(const SgpArgs* args, int pub_grid, uint32_t* host_f
                              cudaStream_t stream)
 {
     sgp_probe_kernel<<<1, SGP_THREADS, 0, stream>>>(*args, pub_grid, host_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_gather_wait(const SgpArgs* args, int pub_grid, cudaStream_t stream)
+{
+    sgp_gather_wait_kernel<<<1, SGP_THREADS, 0, stream>>>(*args, pub_grid);
+    return cudaGetLastError();
+}
+
+cudaError_t sgp_launch_gather_ack(const SgpArgs* args, cudaStream_t stream)
+{
+    sgp_gather_ack_kernel<<<1, 1, 0, stream>>>(*args);
     return cudaGetLastError();
 }
 

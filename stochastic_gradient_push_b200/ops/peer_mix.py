@@ -66,7 +66,8 @@ class GossipEngine(object):
                  with_residual: bool = False,
                  grid: Optional[int] = None, gather_grid: Optional[int] = None,
                  timeout_s: float = 30.0, name: str = 'sgp', segments: int = 4,
-                 gather_tma: bool = True, soft_timeout_s: Optional[float] = None):
+                 gather_tma: bool = True, soft_timeout_s: Optional[float] = None,
+                 gather_dma: Optional[bool] = None):
         C = native.load()
         self.C = C
         self.world = world
@@ -100,6 +101,9 @@ class GossipEngine(object):
         soft = timeout_s / 10.0 if soft_timeout_s is None else soft_timeout_s
         self._state_i32[C.STATE_OFF_SOFT_TIMEOUT_US // 4] = int(min(max(soft, 0.0) * 1e6, 2 ** 31 - 1))
         self._soft_seen = 0
+        self._state_f32[C.STATE_OFF_RES_SCALE // 4] = 1.0
+        self._phase_base = 0            # host mirror of SgpState::phase_base
+        self._gather_dma_pref = gather_dma
         self.hyper = torch.zeros(C.HYPER_FLOATS, dtype=torch.float32, device=self.device)
         # ring of pinned staging rows: an lr change must not rewrite host memory that an earlier,
         # still-queued async H2D copy is going to read
@@ -131,6 +135,7 @@ class GossipEngine(object):
         self.gather_tma = bool(gather_tma)
         self.steps = 0               # host mirror of SgpState.step
         self._graph_synced = 0       # rotations applied to the python graph object
+        self._refresh_in_peers()
         self.set_hyper(0.0, 0.0, 0.0, False, do_sgd=False)
         torch.cuda.synchronize(self.device)
         world.barrier()
@@ -167,6 +172,8 @@ class GossipEngine(object):
         self.period = table.shape[0]
         want = self.graph.phase_index()
         base = (want - self.steps) % self.period
+        self._phase_base = int(base)
+        self._refresh_in_peers()
         self._state_i32[C.STATE_OFF_PHASE_BASE // 4] = int(base)
         self._state_i32[C.STATE_OFF_ACK_FROM // 4] = int(self.steps)
         self._graph_synced = self.steps
@@ -209,9 +216,39 @@ class GossipEngine(object):
         self.ctx.step(f, self.grid)
         self.steps += 1
 
-    def gather(self, tma=None):
-        """residual <- sum_k in_w[k] * outbox_k (Overlap-SGP side stream); TMA bulk
-        copies by default, register-staged loads with ``tma=False``."""
+    def _refresh_in_peers(self):
+        """in-neighbour per phase (host side) and whether the Overlap-SGP gather can run on the
+        copy engines: that needs exactly one in-neighbour in every phase (then the residual is a
+        plain copy of its outbox; the edge weight is applied when the residual is folded)."""
+        phases = self.graph.phases()
+        if not self.graph.is_dynamic_graph():
+            phases = phases[:1] * max(1, self.period)
+        self._in_peers = [list(ins) for _, ins in phases]
+        eligible = self.nranks > 1 and all(len(ins) == 1 for ins in self._in_peers) \
+            and len(self._in_peers) == self.period
+        pref = self._gather_dma_pref
+        if pref is None:
+            import os
+            pref = os.environ.get('SGP_B200_GATHER_DMA', '1') != '0'     # A/B switch
+        self.gather_dma = bool(pref and eligible)
+
+    def dma_key(self):
+        """(schedule row, outbox parity) of the NEXT overlap step: what a captured CUDA graph with a
+        DMA gather is specific to (the copy's source address is baked into the graph)"""
+        return ((self.steps + self._phase_base) % self.period, self.steps & 1)
+
+    def gather(self, tma=None, dma=None):
+        """residual <- sum_k in_w[k] * outbox_k (Overlap-SGP side stream).  With one in-neighbour
+        per step (the default schedules) this is a COPY-ENGINE transfer of the peer's outbox bracketed
+        by a 1-CTA flag wait and a 1-thread ack kernel -- no SM is taken away from the forward pass;
+        otherwise a gather kernel (TMA bulk copies by default, register-staged with ``tma=False``)."""
+        use_dma = self.gather_dma if dma is None else (bool(dma) and self.gather_dma)
+        if use_dma:
+            s = self.steps - 1                       # publish() of this step already advanced the mirror
+            j = self._in_peers[(s + self._phase_base) % self.period][0]
+            src = self.outbox.peers[j].data_ptr() + (s & 1) * self.n * 4
+            self.ctx.gather_dma(self.grid, int(src))
+            return
         self.ctx.gather(self.gather_grid, self.grid, self.gather_tma if tma is None else bool(tma))
 
     def local(self, sgd=False, fold=False, zero_grad=True, in_numerator=False):
@@ -334,6 +371,12 @@ class GossipEngine(object):
         of the value itself, but reads the step counter)."""
         off = self.C.STATE_OFF_PSW // 4
         return self._state_f32[off + (self.device_step & 1): off + (self.device_step & 1) + 1]
+
+    @property
+    def res_scale(self) -> float:
+        """factor the pending residual buffer is multiplied with when folded (1 after a gather
+        kernel; the in-neighbour's edge weight after a copy-engine gather)"""
+        return float(self._state_f32[self.C.STATE_OFF_RES_SCALE // 4].item())
 
     @property
     def res_weight(self) -> float:

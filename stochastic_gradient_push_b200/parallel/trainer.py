@@ -86,6 +86,8 @@ class GossipTrainer(object):
         # kernels of OUR extension in one training step (counted over the graph capture, or over
         # the last eager step): what bench.py reports as gpu_launches / step
         self.own_launches_per_step = None
+        self._graphs = {}               # overlap + DMA gather: one captured graph per (row, parity)
+        self._pool = None
 
     # ------------------------------------------------------------------ #
     def _autocast(self):
@@ -264,8 +266,23 @@ class GossipTrainer(object):
         with torch.cuda.stream(self.stream):
             self._run_on_stream()
 
+    def _graph_key(self):
+        """Overlap-SGP with the copy-engine gather: the source address of the DMA copy (which
+        in-neighbour, which outbox half) is baked into a captured graph, so there is one graph per
+        (schedule row, parity) -- lcm(period, 2) of them, sharing one memory pool."""
+        if self.overlap and self.gossip and self.model.gossip_enable \
+                and getattr(self.engine, 'gather_dma', False):
+            return self.engine.dma_key()
+        return None
+
     def _run_on_stream(self):
         self._set_lr()
+        key = self._graph_key()
+        if key is not None and self._graphs:
+            if key not in self._graphs:           # first visit of this (row, parity): capture it
+                self.graph = None
+                self._capture()
+            self.graph = self._graphs[key]
         if self.graph is not None:
             self.graph.replay()
             self._after_replay()
@@ -296,10 +313,16 @@ class GossipTrainer(object):
         torch.cuda.synchronize(self.device)
         steps_before = self.engine.steps
         self.graph = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()      # shared by the per-(row, parity) graphs
+        key = self._graph_key()
         c0 = self.engine.C.launch_count()
-        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode='thread_local'):
+        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode='thread_local',
+                              pool=self._pool):
             self._one_step(first=False)
         self.own_launches_per_step = self.engine.C.launch_count() - c0
+        if key is not None:
+            self._graphs[key] = self.graph
         # capture does not execute: undo the host-side step mirror advance
         self.engine.steps = steps_before
         torch.cuda.synchronize(self.device)

@@ -118,6 +118,13 @@ def test_loopback_graphed_trainer_equals_eager(algo):
                                        overlap=(algo == 'osgp'), rank=r, world_size=n, heartbeat_timeout=20,
                                        symmetric_world=lw.view(r), transport='nvlink', grid=4, symmetric_name='loopback')
             opt = FusedGossipSGD(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+            if use_graph:
+                # the copy-engine gather needs one graph per (row, parity), captured on first use;
+                # a capture synchronises the device, which virtual ranks sharing one GPU cannot do
+                # mid-step -> this test exercises the kernel gather under graphs (the DMA gather
+                # runs in the eager loop-back tests above and in the multi-process tests)
+                model.engine._gather_dma_pref = False
+                model.engine._refresh_in_peers()
             trainers.append(GossipTrainer(model, opt, amp_dtype=None, use_cuda_graph=use_graph, warmup_iters=10 ** 6))
         gens = [torch.Generator().manual_seed(100 + r) for r in range(n)]
         for s in range(steps):

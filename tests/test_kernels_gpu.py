@@ -178,12 +178,20 @@ def test_bf16_grads_and_shadow():
         assert e.grad.float().abs().sum().item() == 0.0
 
 
-def test_overlap_publish_gather_fold_matches_oracle():
+@pytest.mark.parametrize('dma', [True, False], ids=['copy-engine-gather', 'kernel-gather'])
+def test_overlap_publish_gather_fold_matches_oracle(dma):
     """OSGP arithmetic: x <- x - lr*dir ; x += residual ; publish ; residual of
-    step k is folded at step k+1 (1-step stale)."""
+    step k is folded at step k+1 (1-step stale).  The gather runs either on the copy engines
+    (flag-wait kernel + cudaMemcpyAsync of the in-neighbour's outbox + ack kernel; the edge weight
+    is applied at fold time) or as the TMA gather kernel."""
     n, numel, steps = 4, 2 * CHUNK, 6
     engines, graphs, _, streams = _mk_world(n, numel, sgp.NPeerDynamicDirectedExponentialGraph,
                                             1, overlap=True)
+    for e in engines:
+        assert e.gather_dma                     # one in-neighbour per phase: eligible
+        e._gather_dma_pref = dma
+        e._refresh_in_peers()
+        assert e.gather_dma == dma
     side = [torch.cuda.Stream() for _ in range(n)]
     ogs, oms = _oracle_graphs(graphs)
     lr, mu, wd, nest = 0.1, 0.9, 1e-4, False
@@ -229,7 +237,7 @@ def test_overlap_publish_gather_fold_matches_oracle():
         for i, e in enumerate(engines):
             e.check()
             torch.testing.assert_close(e.z.double(), zs[i], rtol=1e-5, atol=1e-5)
-            torch.testing.assert_close(e.residual.double(), res[i], rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(e.residual.double() * e.res_scale, res[i], rtol=1e-5, atol=1e-5)
             assert abs(e.ps_weight - ws[i]) < 1e-6
             assert abs(e.res_weight - wres[i]) < 1e-6
     # flush: fold the last residual without publishing
