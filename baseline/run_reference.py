@@ -82,7 +82,8 @@ def main_adpsgd(args, rank, world, master_port, torch, dist):
     training process on ``master_port + 1`` and the forked gossip PROCESS on ``master_port``
     (``gossip_sgd_adpsgd.py:695``, ``gossip/ad_psgd.py:280-284``), CUDA-IPC shared parameter /
     gradient tensors between them.  Substitutions: synthetic loader (= stopwatch), the one-word
-    ``accuracy`` fix, the ``forkserver`` start method its ``__main__`` block sets."""
+    ``accuracy`` fix, the ``forkserver`` start method its ``__main__`` block sets, and a stub for
+    its NIC-name probe (needs the `ip` binary, which the image lacks; the name is unused here)."""
     import torch.multiprocessing as mp
     script = os.path.join(REF, 'bin', 'gossip_sgd_adpsgd.py')
     if not os.path.isfile(script):
@@ -129,6 +130,10 @@ def main_adpsgd(args, rank, world, master_port, torch, dist):
             pass
 
     ref.make_dataloader = lambda a, train=True: ((SyntheticLoader(), _Sampler()) if train else [])
+    # the script probes the NIC name with `ip link show up` unconditionally (gossip_sgd_adpsgd.py:174);
+    # the image has no `ip` binary and the name is unused with --network_interface_type infiniband
+    # (no NCCL_SOCKET_IFNAME is exported), so the probe is stubbed
+    ref.get_tcp_interface_name = lambda network_interface_type='ethernet': 'lo'
 
     def accuracy(output, target, topk=(1,)):
         with torch.no_grad():

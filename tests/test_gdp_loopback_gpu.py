@@ -72,7 +72,9 @@ def _run(n, graph_name, ppi, steps, overlap, fused, nesterov, ppi_switch=None):
     ('NPeerDynamicDirectedExponentialGraph', 1, False, False, True),
     ('DynamicDirectedExponentialGraph', 2, False, True, False),
     ('NPeerDynamicDirectedExponentialGraph', 1, True, True, False),
-    ('NPeerDynamicDirectedExponentialGraph', 1, True, False, False),
+    # (overlap + an external torch.optim optimizer is covered by the multi-process test only: its
+    # host-side numerator / de-bias scaling reads the device step, and those host syncs of one
+    # virtual rank wait on kernels of ranks the single host thread has not launched yet)
     ('RingGraph', 1, False, True, True),
 ])
 def test_loopback_world_matches_simulation(graph_name, ppi, overlap, fused, nesterov):
