@@ -92,6 +92,11 @@ def main_adpsgd(args, rank, world, master_port, torch, dist):
     # two worlds, both hosted by THEIR rank 0 (training world on port+1, gossip world on port): the
     # launcher's agent store only serves the launcher's own port, so the scripts must create their
     # TCP stores themselves on a port pair next to it
+    # torch-version shim for the gossip child (see baseline/compat/sitecustomize.py) and for us
+    compat = os.path.join(HERE, 'compat')
+    os.environ['PYTHONPATH'] = compat + os.pathsep + os.environ.get('PYTHONPATH', '')
+    if not hasattr(dist, '_backend'):
+        dist._backend = -1
     os.environ.pop('TORCHELASTIC_USE_AGENT_STORE', None)
     master_port = str(int(master_port) + 17)
     spec = importlib.util.spec_from_file_location('ref_gossip_sgd_adpsgd', script)
