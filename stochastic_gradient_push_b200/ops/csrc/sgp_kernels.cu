@@ -962,6 +962,7 @@ __global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, con
 
     int ready = 0;
     if (engaged) {
+        __shared__ int s_stop;
         const unsigned long long t0 = globaltimer_ns();
         while (true) {
             if (threadIdx.x == 0) s_all = 1;
@@ -973,9 +974,14 @@ __global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, con
                     if ((int32_t)(ld_acquire_sys(&a.pads[j]->pub_seq[f]) - want) < 0) s_all = 0;
             }
             __syncthreads();
-            ready = s_all;
+            // ONE thread decides whether to stop (the deadline must not be evaluated per thread:
+            // threads straddling it would leave the barrier loop at different iterations)
+            if (threadIdx.x == 0) s_stop = (s_all != 0) || (globaltimer_ns() - t0 > max_wait_ns);
             __syncthreads();
-            if (ready || globaltimer_ns() - t0 > max_wait_ns) break;
+            ready = s_all;
+            const int stop = s_stop;
+            __syncthreads();                  // s_all / s_stop are rewritten by the next iteration
+            if (stop) break;
             __nanosleep(500);
         }
     }
