@@ -53,6 +53,8 @@ def parse():
     ap.add_argument('--dtype', default='fp32', choices=['bf16', 'fp32'],
                     help='fp32 (default): fp32 activations / weights with TF32 tensor-core convolutions, '
                          'the precision of the reference arm; bf16: reported as a labelled secondary line')
+    ap.add_argument('--secondary', action='store_true',
+                    help='also measure the secondary lines when --gpus > 1 (default: single-GPU runs only)')
     ap.add_argument('--no-secondary', action='store_true',
                     help='skip the secondary (other precision / per-GPU batch 32) measurements')
     ap.add_argument('--model', default='resnet50')
@@ -258,7 +260,7 @@ def measure(args, dtype, bs, K, W, rank, world, dev, sample_clocks):
     # SGD-only fused kernel), timed the same way on the same GPUs right after -- the difference is
     # what gossip costs per step after all overlap (kernel time + waiting for the in-neighbours)
     exposed = None
-    if world > 1 and args.algo != 'ar' and not args.skip_local:
+    if world > 1 and args.algo != 'ar' and not args.skip_local and sample_clocks:   # (main measurement only)
         g_gossip = trainer.graph
         if args.algo == 'adpsgd':
             g_local = g_gossip               # the captured graph is forward/backward only
@@ -350,7 +352,10 @@ def run_ours(args):
     # reference's per-GPU batch (32 images per GPU in its 8-GPU-per-node job scripts), where the
     # gossip step is a larger share of the iteration
     secondary = {}
-    if not args.no_secondary:
+    # (multi-GPU runs measure the headline configuration only -- one model / one symmetric-memory
+    # rendezvous per process; pass --secondary to force the extra lines there.  Batch-32 and bf16
+    # multi-GPU numbers: profiles/bench_r2_n2_*_bs32_*, profiles/bench_n8_sgp_bs32_r2_fp32.json)
+    if not args.no_secondary and (world == 1 or args.secondary):
         other = 'bf16' if args.dtype == 'fp32' else 'fp32'
         for key, (dt, b) in (('%s_bs%d' % (other, bs), (other, bs)), ('%s_bs32' % args.dtype, (args.dtype, 32))):
             if (dt, b) == (args.dtype, bs):
