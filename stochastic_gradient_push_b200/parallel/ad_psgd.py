@@ -71,10 +71,9 @@ class BilatGossipDataParallel(Module):
             device_ids = [first.device.index] if on_cuda else []
         self.device_ids = list(device_ids)
         self.output_device = self.device_ids[0] if self.device_ids else None
-        assert len(self.device_ids) <= 1, \
-            'one process per GPU: wrap each replica in its own rank'
         self.module = module
         self._module_copies = [self.module]
+        self._replicas = None           # single-process multi-GPU mode (device_ids with > 1 GPU)
 
         # control plane: reuse the caller's process group, or create the one the
         # reference's gossip process would have created (ad_psgd.py:280-284)
@@ -133,6 +132,13 @@ class BilatGossipDataParallel(Module):
         self.arena.adopt(params)
         self.grad_flat = self.arena.new_buffer()
         self.arena.bind_grads(params, self.grad_flat)
+        if len(self.device_ids) > 1:
+            # the reference's launch mode (one process, several GPUs; gossip/ad_psgd.py:57-69,
+            # 148-191, 378-404): flat-arena replicas, P2P DMA parameter sync, one P2P kernel that
+            # sums the replicas' gradients into the master's before they go to the gossip side
+            from .replicas import LocalReplicas
+            self._replicas = LocalReplicas(module, self.device_ids, self.arena, params)
+            self._module_copies = self._replicas.copies
 
         # gossip copy + its gradient / momentum buffers
         self.gossip_flat = self.arena.new_buffer()
@@ -231,11 +237,15 @@ class BilatGossipDataParallel(Module):
         if self.device_ids:
             from torch.nn.parallel.scatter_gather import scatter_kwargs
             inputs, kwargs = scatter_kwargs(inputs, kwargs, self.device_ids, dim=0)
+            if self._replicas is not None and len(inputs) > 1:
+                return self._replicas.forward(inputs, kwargs, self.output_device)
             return self.module(*inputs[0], **kwargs[0])
         return self.module(*inputs, **kwargs)
 
     def train(self, mode=True):
         super(BilatGossipDataParallel, self).train(mode)
+        if self._replicas is not None:
+            self._replicas.train(mode)
         return self
 
     def eval(self):
@@ -512,6 +522,8 @@ class BilatGossipDataParallel(Module):
 
     def __make_backward_hook(self):
         def hook(*unused):
+            if self._replicas is not None:          # sum the local replicas' gradients first
+                self._replicas.reduce_grads(self.grad_flat)
             self._transfer_grads()
             self._pull_model()
 

@@ -535,3 +535,45 @@ def test_hierarchical_mode_runs_on_nvls_kernels():
     if not _nvls_supported():
         pytest.skip('no NVSwitch multicast')
     assert all(run_distributed(_hier_nvls_worker, 2, 4, backend='nccl', timeout=300))
+
+
+def test_adpsgd_single_process_multi_gpu_replicas():
+    """reference launch mode for AD-PSGD (one process, several GPUs; gossip/ad_psgd.py:57-69,
+    148-191, 378-404): the replicas' gradients are summed into the master's by the P2P kernel before
+    they are handed to the gossip side, whose fused SGD must then equal plain SGD on the whole batch."""
+    import copy
+    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel
+    if _ngpu() < 2:
+        pytest.skip('needs 2 GPUs')
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).to(dev)
+    ref = copy.deepcopy(net)
+    model = BilatGossipDataParallel(net, device_ids=[0, 1], rank=0, world_size=1, lr=0.05, momentum=0.9,
+                                    weight_decay=0.0, nesterov=True, verbose=False, heartbeat_timeout=20)
+    assert model._replicas is not None and len(model._module_copies) == 2
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+    model.train()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    try:
+        for _ in range(5):
+            x = torch.randn(24, 16, device=dev, generator=g)
+            y = torch.randn(24, 4, device=dev, generator=g)
+            out = model(x)
+            assert out.shape == (24, 4) and out.device == dev
+            (((out - y) ** 2).sum() / 24).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+            (((ref(x) - y) ** 2).sum() / 24).backward()
+            ropt.step()
+            ropt.zero_grad()
+        model.eval()                       # pulls the gossip copy into the training copy
+        torch.cuda.synchronize()
+        model._check()
+        assert model.grads_applied == 5
+        for p, q in zip(net.parameters(), ref.parameters()):
+            torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
+    finally:
+        model.shutdown()
