@@ -12,8 +12,10 @@ epoch reaches ``--num_epochs`` (:267-309).
 
 Differences: one control-plane process group is enough (the reference needs
 ``master_port`` and ``master_port+1`` because its gossip *process* owns a second
-world); the gossip loop is a thread + low-priority stream on the same GPU
-(see ``parallel/ad_psgd.py``).
+world); on the kernel data plane the gossip loop is a native (GIL-free) daemon thread
+enqueueing a device-side round state machine on a lowest-priority stream of the same
+GPU, on the c10d data plane a Python thread over isend / irecv (see
+``parallel/ad_psgd.py``).
 """
 
 from __future__ import annotations
