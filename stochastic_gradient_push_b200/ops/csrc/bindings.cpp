@@ -402,7 +402,17 @@ public:
         fb_dev_ = reinterpret_cast<uint32_t*>(dp);
         for (int i = 0; i < 8; ++i) SGP_CUDA_CHECK(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
     }
-    ~BilatDaemon() { stop(); }
+    ~BilatDaemon()
+    {
+        stop();
+        // the thread has drained the stream; release what the constructor created (errors are
+        // ignored: at interpreter exit the CUDA context may already be gone)
+        for (int i = 0; i < 8; ++i)
+            if (events_[i]) cudaEventDestroy(events_[i]);
+        if (stream_) cudaStreamDestroy(stream_);
+        if (fb_host_) cudaFreeHost(const_cast<uint32_t*>(fb_host_));
+        cudaGetLastError();
+    }
 
     void start()
     {

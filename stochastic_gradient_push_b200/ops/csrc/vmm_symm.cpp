@@ -22,11 +22,15 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <poll.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/syscall.h>
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <cerrno>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -214,6 +218,9 @@ public:
     {
         if (fd_ >= 0) close(fd_);
         if (mc_fd_ >= 0) close(mc_fd_);
+        if (have_mc_ && !mc_map_) {          // created / imported but never bound + mapped
+            try { DRV(cuMemRelease); cuMemRelease_(mc_); } catch (...) {}
+        }
     }
 
     int fd() const { return fd_; }
@@ -348,10 +355,29 @@ public:
     }
 
     // -> (sender rank, tag, fd usable in this process)
-    py::tuple recv()
+    // (a rank that never sends -- crashed, or stuck before its rendezvous -- surfaces as an
+    // exception after `timeout_s`, not as a hang; the GIL is released while waiting)
+    py::tuple recv(double timeout_s)
     {
-        const int c = accept(sock_, nullptr, nullptr);
+        int c = -1;
+        {
+            py::gil_scoped_release nogil;
+            pollfd pf;
+            pf.fd = sock_;
+            pf.events = POLLIN;
+            pf.revents = 0;
+            const int ms = timeout_s <= 0 ? -1 : (int)std::min(timeout_s * 1e3, 2.0e9);
+            int r;
+            do { r = poll(&pf, 1, ms); } while (r < 0 && errno == EINTR);
+            if (r > 0) c = accept(sock_, nullptr, nullptr);
+            else if (r == 0) c = -2;
+        }
+        if (c == -2) throw std::runtime_error("fd channel: timed out waiting for a peer's descriptor");
         if (c < 0) throw std::runtime_error("fd channel: accept failed");
+        timeval tv;
+        tv.tv_sec = 30;
+        tv.tv_usec = 0;
+        setsockopt(c, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
         int payload[2] = {-1, -1};
         iovec iov = {payload, sizeof(payload)};
         char ctrl[CMSG_SPACE(sizeof(int))];
@@ -383,7 +409,7 @@ void bind_vmm(py::module& mod)
     py::class_<FdChannel, std::shared_ptr<FdChannel>>(mod, "FdChannel")
         .def(py::init<const std::string&, int, int>(), py::arg("job"), py::arg("rank"), py::arg("world"))
         .def("send", &FdChannel::send, py::call_guard<py::gil_scoped_release>())
-        .def("recv", &FdChannel::recv);
+        .def("recv", &FdChannel::recv, py::arg("timeout_s") = 300.0);
     mod.def("close_fd", &close_fd);
     mod.def("vmm_caps", &vmm_caps, "multicast / handle-type capabilities of a device");
     mod.def("vmm_padded_size", &vmm_padded_size);

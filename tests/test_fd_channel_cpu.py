@@ -67,3 +67,17 @@ def test_payload_is_readable_through_the_received_descriptor():
     assert (src, tag) == (0, 7) and fd != r
     assert os.read(fd, 16) == b'payload'
     C.close_fd(fd)
+
+
+def test_recv_times_out_instead_of_hanging_when_a_peer_never_sends():
+    import time
+    try:
+        from stochastic_gradient_push_b200.ops import native
+        C = native.load()
+    except Exception as e:
+        pytest.skip('native extension unavailable: %s' % e)
+    ch = C.FdChannel('sgp_b200_timeout.%d' % os.getpid(), 0, 2)
+    t0 = time.time()
+    with pytest.raises(RuntimeError, match='timed out'):
+        ch.recv(timeout_s=0.3)
+    assert 0.25 < time.time() - t0 < 5.0
