@@ -95,9 +95,11 @@ class VmmSymmetricWorld(SymmetricWorld):
     view (``_C.VmmBuffer``, csrc/vmm_symm.cpp): ``alloc()`` returns a buffer whose ``peers`` /
     ``table`` are ordinary unicast P2P mappings (same contract as :class:`SymmetricWorld`) and
     whose ``mc`` is a tensor over the multicast address -- ``multimem.ld_reduce`` reads through it
-    are summed inside the switch, ``multimem.st`` writes land in every GPU.  POSIX file
-    descriptors of the allocations travel as integers over the c10d control plane and are
-    duplicated with ``pidfd_getfd`` (single host, one NVLink domain)."""
+    are summed inside the switch, ``multimem.st`` writes land in every GPU.  The POSIX file
+    descriptors of the allocations are passed between the ranks with ``SCM_RIGHTS`` messages over
+    abstract unix-domain sockets (``_C.FdChannel``; ``pidfd_getfd`` is refused inside GPU
+    containers), named after a job token that travels over the c10d control plane (single host,
+    one NVLink domain)."""
 
     @staticmethod
     def supported(device=None) -> bool:
