@@ -947,7 +947,8 @@ __global__ void sgp_gather_ack_kernel(const SgpArgs a)
 __global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, const int passive,
                                         const unsigned long long max_wait_ns, uint32_t* host_fb)
 {
-    __shared__ int s_all;
+    __shared__ int s_all, s_stop;
+    __shared__ uint32_t s_published, s_may_start;
     SgpState* st = a.st;
     const uint32_t step = *((volatile uint32_t*)&st->step);
     RowInfo row;
@@ -955,14 +956,21 @@ __global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, con
     int segs = a.segments < 1 ? 1 : a.segments;
     if (segs > SGP_SEQ_STRIDE - 1) segs = SGP_SEQ_STRIDE - 1;
     const uint32_t want = step * (uint32_t)SGP_SEQ_STRIDE + (uint32_t)segs;
-    const uint32_t published = *((volatile uint32_t*)&st->bilat_published);
-    const bool may_start = (*((volatile uint32_t*)&st->bilat_enabled) != 0u) &&
-                           (*((volatile uint32_t*)&st->bilat_budget) != 0u);
+    // bilat_budget / bilat_enabled are rewritten asynchronously (sgp_bilat_ctl_kernel on the
+    // training stream): ONE thread samples them and the whole CTA uses that sample, so that every
+    // thread takes the same branch around the barrier loop below
+    if (threadIdx.x == 0) {
+        s_published = *((volatile uint32_t*)&st->bilat_published);
+        s_may_start = ((*((volatile uint32_t*)&st->bilat_enabled) != 0u) &&
+                       (*((volatile uint32_t*)&st->bilat_budget) != 0u)) ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t published = s_published;
+    const bool may_start = s_may_start != 0u;
     const bool engaged = published != 0u || may_start;
 
     int ready = 0;
     if (engaged) {
-        __shared__ int s_stop;
         const unsigned long long t0 = globaltimer_ns();
         while (true) {
             if (threadIdx.x == 0) s_all = 1;
@@ -1006,8 +1014,9 @@ __global__ void sgp_bilat_decide_kernel(const SgpArgs a, const int pub_grid, con
     else if (do_pull)
         cmd = SGP_F_PHASE2 | SGP_F_PUBLISH | SGP_F_SELF_FROM_Z;
     if (do_publish) {                          // starting a round consumes budget
+        // (compare-and-swap: a budget that sgp_bilat_ctl_kernel rewrote in the meantime wins)
         const uint32_t bud = *((volatile uint32_t*)&st->bilat_budget);
-        if (bud != 0xFFFFFFFFu && bud > 0u) st->bilat_budget = bud - 1u;
+        if (bud != 0xFFFFFFFFu && bud > 0u) atomicCAS(&st->bilat_budget, bud, bud - 1u);
     }
     st->bilat_cmd = cmd;
     st->bilat_done = (uint32_t)ready;
