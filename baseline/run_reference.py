@@ -151,6 +151,33 @@ def main_adpsgd(args, rank, world, master_port, torch, dist):
 
     ref.accuracy = accuracy
     t_all = time.time()
+
+    # the reference's training process waits forever on its gossip process's flags
+    # (gossip/ad_psgd.py:237-249); if that child dies (it does on current PyTorch without the shim
+    # above) or nothing completes in time, report `unavailable` instead of hanging the harness
+    limit_s = float(os.environ.get('SGP_REF_ADPSGD_LIMIT_S', 600))
+
+    def _watchdog():
+        seen_child = False
+        while watch.ms is None:
+            time.sleep(1.0)
+            kids = mp.active_children()
+            seen_child = seen_child or bool(kids)
+            why = None
+            if seen_child and not kids:
+                why = 'the reference gossip process exited before the timed region completed'
+            elif time.time() - t_all > limit_s:
+                why = 'reference AD-PSGD run did not complete within %d s' % int(limit_s)
+            if why is not None:
+                if rank == 0:
+                    print(json.dumps({'impl': 'reference', 'unavailable': why}))
+                    sys.stdout.flush()
+                for child in kids:
+                    child.terminate()
+                os._exit(0)
+
+    import threading
+    threading.Thread(target=_watchdog, name='ref-adpsgd-watchdog', daemon=True).start()
     try:
         ref.main()
     except _TimedRegionDone:
