@@ -42,19 +42,52 @@ from .mixing_manager import MixingManager, UniformMixing
 # --------------------------------------------------------------------------- #
 class C10dTransport(object):
     """isend/irecv on a c10d group.  Tags disambiguate repeated edges between
-    the same pair inside one step (phone books may contain duplicates)."""
+    the same pair inside one step (phone books may contain duplicates).
+
+    NCCL (GPU tensors between hosts) needs two things gloo does not:
+
+    * a rank's receives and sends of ONE exchange must be launched as ONE group
+      (``batch_isend_irecv``): NCCL runs the point-to-point operations of a pair of ranks on
+      one stream in launch order, so "irecv then isend" on both sides of a symmetric exchange
+      (a ring of 2, the ``n/2`` hop of the exponential graphs, every bipartite pairing) would
+      leave both receive kernels waiting for sends that are queued behind them.
+      ``exchange()`` does that when ``batched`` (default: the group's backend is NCCL);
+    * sends and receives that are NOT issued together (the AD-PSGD loop sends early and
+      receives when the partner has answered) must not share a communicator per direction:
+      with ``reverse_group`` set, messages from a higher to a lower rank travel on that
+      second group, so the two directions of a pair never queue behind each other.
+
+    NCCL ignores tags; repeated edges are matched in posting order, which is the same
+    (``k``-th send <-> ``k``-th receive) on both sides."""
 
     name = 'c10d'
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, batched=None, reverse_group=None):
         self.group = group
+        self.reverse_group = reverse_group
+        self._batched = batched
+
+    @property
+    def batched(self) -> bool:
+        if self._batched is None:
+            try:
+                self._batched = bool(dist.is_initialized()) and \
+                    str(dist.get_backend(self.group)).lower() == 'nccl'
+            except Exception:
+                self._batched = False
+        return self._batched
+
+    def _group_for(self, src, dst):
+        if self.reverse_group is not None and src > dst:
+            return self.reverse_group
+        return self.group
 
     def post_recvs(self, buffers, in_edges):
         reqs, seen = [], {}
         for buf, edge in zip(buffers, in_edges):
             k = seen.get(edge.src, 0)
             seen[edge.src] = k + 1
-            reqs.append(dist.irecv(buf, src=edge.src, group=self.group, tag=k))
+            reqs.append(dist.irecv(buf, src=edge.src, group=self._group_for(edge.src, edge.dest), tag=k))
         return reqs
 
     def post_sends(self, msgs, out_edges):
@@ -62,14 +95,37 @@ class C10dTransport(object):
         for msg, edge in zip(msgs, out_edges):
             k = seen.get(edge.dest, 0)
             seen[edge.dest] = k + 1
-            reqs.append(dist.isend(msg, dst=edge.dest, group=self.group, tag=k))
+            reqs.append(dist.isend(msg, dst=edge.dest, group=self._group_for(edge.src, edge.dest), tag=k))
         return reqs
+
+    def exchange(self, recv_bufs, in_edges, send_msgs, out_edges):
+        """Post the receives and the sends of one step -> ``(recv_reqs, send_reqs)``.  Every
+        request of ``recv_reqs`` must be waited for before ANY receive buffer is read (a batched
+        launch returns requests that cover the whole group, not one per buffer)."""
+        if not self.batched:
+            return self.post_recvs(recv_bufs, in_edges), self.post_sends(send_msgs, out_edges)
+        # (a grouped launch takes ONE process group; the direction split is pointless inside it)
+        ops, seen = [], {}
+        for buf, edge in zip(recv_bufs, in_edges):
+            k = seen.get(edge.src, 0)
+            seen[edge.src] = k + 1
+            ops.append(dist.P2POp(dist.irecv, buf, edge.src, self.group, tag=k))
+        seen = {}
+        for msg, edge in zip(send_msgs, out_edges):
+            k = seen.get(edge.dest, 0)
+            seen[edge.dest] = k + 1
+            ops.append(dist.P2POp(dist.isend, msg, edge.dest, self.group, tag=k))
+        if not ops:
+            return [], []
+        return list(dist.batch_isend_irecv(ops)), []
 
     def post_polled_recv(self, buf, in_edge):
         """A receive whose completion can be polled without blocking.  gloo's
         ``Work.is_completed()`` never flips until ``wait()`` is called, so a
-        helper thread parks in ``wait()`` and raises an event instead."""
-        return _PolledRecv(self.post_recvs([buf], [in_edge])[0])
+        helper thread parks in ``wait()`` and raises an event instead.  (NCCL works can be
+        polled directly; parking a thread in their stream-level ``wait()`` would return at once.)"""
+        req = self.post_recvs([buf], [in_edge])[0]
+        return req if self.batched else _PolledRecv(req)
 
 
 class _PolledRecv(object):
@@ -315,7 +371,9 @@ class Gossiper(object):
 
         remote_in = [e for e in self.in_edges if e.src != e.dest]
         bufs = self._recv_buffers(len(remote_in))
-        recv_reqs = self.transport.post_recvs(bufs, remote_in)
+        batched = getattr(self.transport, 'batched', False)
+        if not batched:                    # receives first: the peers' messages can land while
+            recv_reqs = self.transport.post_recvs(bufs, remote_in)      # ours are being built
 
         self_msgs, send_edges, send_msgs = [], [], []
         for edge in self.out_edges:
@@ -325,8 +383,13 @@ class Gossiper(object):
             else:
                 send_edges.append(edge)
                 send_msgs.append(m)
-        for req, m in zip(self.transport.post_sends(send_msgs, send_edges),
-                          send_msgs):
+        if batched:                        # NCCL: one grouped launch of all receives and sends
+            # (its requests cover the sends too and are waited for exactly once, below -- a second
+            # wait() on a completed gloo request never returns; `send_msgs` stays alive until then)
+            recv_reqs, send_reqs = self.transport.exchange(bufs, remote_in, send_msgs, send_edges)
+        else:
+            send_reqs = self.transport.post_sends(send_msgs, send_edges)
+        for req, m in zip(send_reqs, send_msgs):
             self.out_msg_buffer.append((req, m))
 
         if loopback is not None:
@@ -335,8 +398,9 @@ class Gossiper(object):
             self.in_msg_buffer.zero_()
         for m in self_msgs:
             self.in_msg_buffer.add_(m)
-        for req, buf in zip(recv_reqs, bufs):
+        for req in recv_reqs:              # all of them before any buffer is read (see exchange())
             req.wait()
+        for buf in bufs:
             self.in_msg_buffer.add_(buf)
 
         self.refresh_peers_()
@@ -389,10 +453,9 @@ class BilatPushPull(Gossiper):
 
         if not self.passive:
             msg = next(self.mix_out_msg_(out_msg, 1., residual=True))
-            recv = self.transport.post_recvs([self.in_msg_buffer], [in_edge])
-            send = self.transport.post_sends([msg], [out_edge])
-            send[0].wait()
-            recv[0].wait()
+            recv, send = self.transport.exchange([self.in_msg_buffer], [in_edge], [msg], [out_edge])
+            for req in send + recv:
+                req.wait()
             completed = True
         else:
             if self._pending_req is None:

@@ -204,14 +204,26 @@ class BilatGossipDataParallel(Module):
                 self.daemon.start()
         else:
             self.gossip_stream = None
-            group = None
+            group = rev_group = None
             if dist.is_initialized() and world_size > 1:
                 group = dist.new_group(list(range(world_size)))   # gossip-only channel
+                import os
+                if str(dist.get_backend(group)).lower() == 'nccl' \
+                        or os.environ.get('SGP_B200_C10D_SPLIT', '0') == '1':      # (test / debug switch)
+                    # this loop sends early and receives once the partner has answered: on NCCL
+                    # the two directions of a pair must not share a communicator (a send queued
+                    # in front of the receive its partner is waiting for would deadlock the pair;
+                    # see gossiper.C10dTransport) -> second group for "higher rank -> lower rank"
+                    rev_group = dist.new_group(list(range(world_size)))
             self._gossip_group = group
             if world_size > 1:
+                # messages are staged on the communication device (pinned host memory for gloo
+                # with a CUDA model, like the reference's comm_device, gossip/ad_psgd.py:351-352)
                 self.gossiper = BilatPushPull(self.gossip_flat, graph=self.graph, mixing=self.mixing,
-                                              rank=rank, world_size=world_size,
-                                              transport=C10dTransport(group), logger=None)
+                                              device=comm_device, rank=rank, world_size=world_size,
+                                              transport=C10dTransport(group, batched=False,
+                                                                      reverse_group=rev_group),
+                                              logger=None)
 
         self.model_meter = Meter(ptag='Model', stateful=True, csv_format=False)
         self.gossip_meter = Meter(ptag='Gossip', stateful=True, csv_format=False)
@@ -468,7 +480,7 @@ class BilatGossipDataParallel(Module):
 
         def publish():
             with self.gossip_lock:
-                snap = self.gossip_flat.clone()
+                snap = self.gossip_flat.to(g.device, copy=True)      # (comm device: see __init__)
             out = g.out_edges[0]
             req = tr.post_sends([snap], [out])[0]
             store.set(key(rnd, out.src, out.dest), '1')

@@ -125,7 +125,10 @@ class _C10dBackend(object):
             n = arena.total + 1
             remote_in = [e for e in in_edges if e.src != e.dest]
             bufs = [self._buf(self.recv_bufs, (dtype, i), n, dtype) for i in range(len(remote_in))]
-            if pollable:     # gloo cannot poll a plain irecv (see _PolledRecv)
+            batched = getattr(self.transport, 'batched', False)   # NCCL: receives + sends as ONE grouped launch
+            if batched:
+                rr = []
+            elif pollable:   # gloo cannot poll a plain irecv (see _PolledRecv)
                 rr = [self.transport.post_polled_recv(b, e) for b, e in zip(bufs, remote_in)]
             else:
                 rr = self.transport.post_recvs(bufs, remote_in)
@@ -145,7 +148,14 @@ class _C10dBackend(object):
                 else:
                     send_edges.append(e)
                     send_msgs.append(msg)
-            reqs += self.transport.post_sends(send_msgs, send_edges)
+            if batched:
+                # (symmetric exchanges -- in-peer == out-peer -- deadlock on NCCL when "irecv, then
+                # isend" is launched op by op on both sides; see gossiper.C10dTransport)
+                rr, _ = self.transport.exchange(bufs, remote_in, send_msgs, send_edges)
+                reqs += rr
+                poll += rr
+            else:
+                reqs += self.transport.post_sends(send_msgs, send_edges)
             recvs.append((arena, bufs + local_add))
             keep.append(send_msgs)
         self.pending = (reqs, recvs, keep, poll)

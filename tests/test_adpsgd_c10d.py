@@ -89,3 +89,21 @@ def test_adpsgd_trains_through_the_gossip_side_optimizer():
     for first, last, applied in out:
         assert last < 0.5 * first, (first, last)
         assert applied >= 55
+
+
+def _split_worker(rank, world, seconds):
+    import os
+    os.environ['SGP_B200_C10D_SPLIT'] = '1'       # what the NCCL backend selects: one group per direction
+    out = _consensus_worker(rank, world, seconds)
+    return out
+
+
+def test_bilateral_gossip_with_one_process_group_per_direction():
+    """the NCCL arrangement of the c10d loop (messages from a higher to a lower rank on a second
+    group, gossiper.C10dTransport) run over gloo: same protocol, same contraction"""
+    world = 4
+    out = run_distributed(_split_worker, world, 20.0, timeout=180)
+    assert min(o[2] for o in out) >= 2
+    vals = [o[0] for o in out]
+    assert all(o[1] < 1e-6 for o in out)
+    assert max(vals) - min(vals) < 1.6 and 0.0 <= min(vals) and max(vals) <= 3.0
