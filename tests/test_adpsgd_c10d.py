@@ -102,7 +102,7 @@ def test_bilateral_gossip_with_one_process_group_per_direction():
     """the NCCL arrangement of the c10d loop (messages from a higher to a lower rank on a second
     group, gossiper.C10dTransport) run over gloo: same protocol, same contraction"""
     world = 4
-    out = run_distributed(_split_worker, world, 20.0, timeout=180)
+    out = run_distributed(_split_worker, world, 6.0, timeout=180)
     assert min(o[2] for o in out) >= 2
     vals = [o[0] for o in out]
     assert all(o[1] < 1e-6 for o in out)
