@@ -446,6 +446,17 @@ class BilatGossipDataParallel(Module):
             self.gossip_read_flag.set()
             self.model_meter.update(time.time() - bt)
 
+    @staticmethod
+    def _bilateral_update(x_now, own_snapshot, partner):
+        """``x <- 1/2 (own_snapshot + partner) + (x_now - own_snapshot)``, in place.  The reference's
+        gossip process cannot apply a gradient between building its message and averaging
+        (one loop iteration, ``gossip/ad_psgd.py:332-361``), so it averages exactly what it sent;
+        here gradients keep landing while a round is in flight, and whatever was applied since the
+        snapshot (``x_now - own_snapshot``) is kept in full instead of being halved."""
+        dev = x_now.device
+        x_now.add_(partner.to(dev) - own_snapshot.to(dev), alpha=0.5)
+        return x_now
+
     def _throttled(self, round_in_flight):
         """True when this rank has done enough rounds since its last gradient and
         is not in the middle of one (a round in flight is always completed)."""
@@ -514,7 +525,7 @@ class BilatGossipDataParallel(Module):
                 sent = publish()
             tr.post_recvs([g.in_msg_buffer], [in_edge])[0].wait()
             with self.gossip_lock:
-                self.gossip_flat.add_(g.in_msg_buffer.to(self.gossip_flat.device)).mul_(0.5)
+                self._bilateral_update(self.gossip_flat, sent[1], g.in_msg_buffer)
             # never block on OUR send: the partner may have gone quiet before
             # posting its receive.  A send is certainly complete once the partner
             # has answered two later rounds, so only those are reaped.

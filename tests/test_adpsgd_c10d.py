@@ -107,3 +107,13 @@ def test_bilateral_gossip_with_one_process_group_per_direction():
     vals = [o[0] for o in out]
     assert all(o[1] < 1e-6 for o in out)
     assert max(vals) - min(vals) < 1.6 and 0.0 <= min(vals) and max(vals) <= 3.0
+
+
+def test_bilateral_update_keeps_gradients_applied_during_a_round():
+    from stochastic_gradient_push_b200.parallel.ad_psgd import BilatGossipDataParallel as B
+    g = torch.Generator().manual_seed(0)
+    own, partner, delta = (torch.randn(9, generator=g) for _ in range(3))
+    # nothing applied since the snapshot: the plain pairwise average of the reference
+    torch.testing.assert_close(B._bilateral_update(own.clone(), own, partner), 0.5 * (own + partner))
+    # a gradient step delta landed between publish and pull: it survives in full
+    torch.testing.assert_close(B._bilateral_update(own + delta, own, partner), 0.5 * (own + partner) + delta)
