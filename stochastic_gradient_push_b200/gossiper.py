@@ -71,8 +71,9 @@ class C10dTransport(object):
     def batched(self) -> bool:
         if self._batched is None:
             try:
+                # ('nccl', or a per-device map such as 'cpu:gloo,cuda:nccl'; grouping is harmless on gloo)
                 self._batched = bool(dist.is_initialized()) and \
-                    str(dist.get_backend(self.group)).lower() == 'nccl'
+                    'nccl' in str(dist.get_backend(self.group)).lower()
             except Exception:
                 self._batched = False
         return self._batched

@@ -208,7 +208,7 @@ class BilatGossipDataParallel(Module):
             if dist.is_initialized() and world_size > 1:
                 group = dist.new_group(list(range(world_size)))   # gossip-only channel
                 import os
-                if str(dist.get_backend(group)).lower() == 'nccl' \
+                if 'nccl' in str(dist.get_backend(group)).lower() \
                         or os.environ.get('SGP_B200_C10D_SPLIT', '0') == '1':      # (test / debug switch)
                     # this loop sends early and receives once the partner has answered: on NCCL
                     # the two directions of a pair must not share a communicator (a send queued
