@@ -17,6 +17,11 @@
 # SIGUSR1 90 s before the time limit -> checkpoint + requeue (ClusterManager):
 #SBATCH --signal=USR1@90
 
+# Gossip unit: by default every GPU is a gossip rank (8 x NB_NODES ranks).  Add
+#   --nprocs_per_node 8
+# to make the NODE the gossip unit, as in the reference (one 8-GPU node = one rank, batch 256):
+# parameters are broadcast and gradients averaged inside the node through the NVSwitch (NVLS
+# kernels), and only the nodes' first ranks gossip over the network.
 export MASTER_ADDR=$(scontrol show hostnames "$SLURM_JOB_NODELIST" | head -n 1)
 export HOSTNAME=$MASTER_ADDR
 

@@ -98,6 +98,12 @@ def build_parser(adpsgd: bool = False) -> argparse.ArgumentParser:
     p.add_argument('--amp', default=True, **B, help='bf16 autocast for forward/backward')
     p.add_argument('--channels_last', default=True, **B)
     p.add_argument('--transport', default='auto', choices=['auto', 'nvlink', 'c10d'])
+    p.add_argument('--nprocs_per_node', default=1, type=int,
+                   help='hierarchical mode (GossipDataParallel(nprocs_per_node=K), reference '
+                        'gossip/distributed.py:62-80; it has no flag for it): K consecutive ranks form a '
+                        'node -- only its first rank gossips, on a graph over the NODES; parameters are '
+                        'broadcast and gradients averaged inside the node every iteration (NVLS kernels on '
+                        'one NVLink domain).  E.g. N hosts x 8 GPUs: --nprocs_per_node 8')
     p.add_argument('--model', default='resnet50')
     p.add_argument('--num_classes', default=1000, type=int)
     p.add_argument('--image_size', default=224, type=int)
@@ -198,8 +204,15 @@ def finalize_args(args, adpsgd=False):
     graph_class = GRAPH_TOPOLOGIES[args.graph_type]
     args.graph_class = graph_class
     args.mixing_class = MIXING_STRATEGIES[args.mixing_strategy]
+    k = max(1, int(getattr(args, 'nprocs_per_node', 1)))
+    args.nprocs_per_node = k
+    if k > 1:
+        assert not adpsgd and not args.all_reduce, '--nprocs_per_node applies to SGP / OSGP / D-PSGD'
+        assert args.world_size % k == 0, '--nprocs_per_node must divide the number of ranks'
     if graph_class is not None and not adpsgd:
-        args.graph = graph_class(args.rank, args.world_size, peers_per_itr=args.ppi_schedule[0])
+        # (hierarchical mode: the graph connects NODES; edges address each node's first rank)
+        args.graph = graph_class(args.rank // k, args.world_size // k, nprocs_per_node=k,
+                                 local_rank=args.rank % k, peers_per_itr=args.ppi_schedule[0])
         if args.mixing_class is not None:
             args.mixing = args.mixing_class(args.graph, args.comm_device)
     return args

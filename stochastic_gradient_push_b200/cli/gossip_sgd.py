@@ -63,7 +63,7 @@ def build_model_and_optimizer(args, log):
         net, graph=args.graph, mixing=args.mixing, comm_device=args.comm_device,
         push_sum=args.push_sum, overlap=args.overlap, synch_freq=args.synch_freq,
         verbose=args.verbose, use_streams=not args.no_cuda_streams, rank=args.rank,
-        world_size=args.world_size, transport=args.transport,
+        world_size=args.world_size, transport=args.transport, nprocs_per_node=args.nprocs_per_node,
         # the captured fast path trains through the bf16 shadow-weight twin (no autocast casts)
         compute_dtype=(torch.bfloat16 if (args.cuda_graph and args.amp and args.fused
                                           and args.device == 'cuda' and args.transport != 'c10d')

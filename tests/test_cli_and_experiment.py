@@ -163,6 +163,32 @@ def test_gossip_sgd_cli_two_ranks_cpu(tmp_path, master_port, extra):
         assert os.path.isfile(str(tmp_path / ('checkpoint_r%d_n2.pth.tar' % r)))
 
 
+@pytest.mark.parametrize('fused', ['False', 'True'])
+def test_gossip_sgd_cli_hierarchical_nprocs_per_node(tmp_path, master_port, fused):
+    """--nprocs_per_node 2 on 4 ranks = 2 nodes: only ranks 0 and 2 gossip (graph over the nodes),
+    their node-mates mirror them at every forward pass.  Every rank writes its CSV / checkpoint;
+    the checkpoints of the two ranks of a node differ by at most the last local step + mix (the
+    snapshot is taken before the next forward re-broadcasts the master's parameters)."""
+    import torch
+    out = _torchrun(4, 'gossip_sgd.py', COMMON + [
+        '--push_sum', 'True', '--graph_type', '5', '--nprocs_per_node', '2', '--fused', fused,
+        '--synthetic_len', '128', '--num_epochs', '1', '--checkpoint_dir', str(tmp_path) + '/',
+        '--num_itr_ignore', '0'], master_port)
+    assert out.returncode == 0, out.stdout[-3000:]
+    sds = []
+    for r in range(4):
+        assert os.path.isfile(str(tmp_path / ('out_r%d_n4.csv' % r)))
+        ck = torch.load(str(tmp_path / ('checkpoint_r%d_n4.pth.tar' % r)), map_location='cpu',
+                        weights_only=False)
+        sd = ck['state_dict']['state_dict']
+        sds.append(torch.cat([v.reshape(-1).float() for k, v in sorted(sd.items())
+                              if 'running' not in k and 'num_batches' not in k]))
+    assert all(torch.isfinite(v).all() for v in sds)
+    torch.testing.assert_close(sds[0], sds[1], rtol=0, atol=2e-2)
+    torch.testing.assert_close(sds[2], sds[3], rtol=0, atol=2e-2)
+    assert 'World-Size,4' in open(str(tmp_path / 'out_r3_n4.csv')).read()
+
+
 def test_gossip_sgd_cli_writes_chrome_trace(tmp_path, master_port):
     """--trace_file: per-rank Chrome trace with forward / backward / optimizer / gossip spans and
     the exposed-communication counter, bounded by --trace_iters."""
