@@ -52,8 +52,15 @@ class AllReduceDataParallel(Module):
         assert all(p.dtype == torch.float32 and p.is_cuda for p in params)
         self.device = params[0].device
         from .symmetric import LocalWorld, SymmetricWorld, VmmSymmetricWorld
+        spans_hosts = False
         if transport == 'auto':
-            transport = 'nvls' if (world_size > 1 and VmmSymmetricWorld.supported(self.device)) else 'p2p'
+            # the NVLS / P2P kernels map every rank's buffers (fd passing, CUDA IPC): one host, one
+            # NVLink domain.  Ranks on several hosts reduce with NCCL and keep the fused local step.
+            from .distributed import _single_nvlink_domain
+            if world_size > 1 and dist.is_initialized() and not _single_nvlink_domain(world_size, True):
+                transport, spans_hosts = 'nccl', True
+            else:
+                transport = 'nvls' if (world_size > 1 and VmmSymmetricWorld.supported(self.device)) else 'p2p'
         if transport == 'nvls' and world_size == 1:
             transport = 'p2p'
         self.transport = transport
@@ -78,7 +85,8 @@ class AllReduceDataParallel(Module):
         C = native.load()
         self.C = C
         if transport != 'nvls':
-            self.world = (SymmetricWorld(self.device) if world_size > 1
+            # (several hosts: nothing is peer-mapped, the buffers below are plain local allocations)
+            self.world = (SymmetricWorld(self.device) if (world_size > 1 and not spans_hosts)
                           else LocalWorld(1, [self.device.index]).view(0))
         n = self.arena.total
         esize = 4 if grad_dtype == torch.float32 else 2
