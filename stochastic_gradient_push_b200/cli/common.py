@@ -94,6 +94,11 @@ def build_parser(adpsgd: bool = False) -> argparse.ArgumentParser:
     p.add_argument('--synthetic', default=None, **B,
                    help='synthetic 3x224x224 data (default: True when --dataset_dir is unset)')
     p.add_argument('--synthetic_len', default=1281167, type=int, help='images per synthetic epoch')
+    p.add_argument('--data_format', default='folder', choices=['folder', 'shards'],
+                   help="folder: torchvision ImageFolder + DataLoader workers (the reference's pipeline); "
+                        "shards: pre-decoded uint8 shards under DATASET_DIR/{train,val} (python -m "
+                        "stochastic_gradient_push_b200.data.make_shards) gathered by a background thread, "
+                        "crop / flip / normalisation on the GPU (data/shards.py)")
     p.add_argument('--fused', default=True, **B, help='FusedGossipSGD (SGD inside the gossip kernel)')
     p.add_argument('--amp', default=True, **B, help='bf16 autocast for forward/backward')
     p.add_argument('--channels_last', default=True, **B)
@@ -297,6 +302,14 @@ def make_dataloader(args, train=True):
         loader = SyntheticLoader(n, args.batch_size, args.world_size if train else 1, args.rank,
                                  args.image_size, args.num_classes, seed=args.seed + (0 if train else 1))
         return (loader, loader) if train else loader
+    if getattr(args, 'data_format', 'folder') == 'shards':
+        from ..data import ShardLoader
+        if train:
+            loader = ShardLoader(os.path.join(args.dataset_dir, 'train'), args.batch_size, args.world_size,
+                                 args.rank, shuffle=True, drop_last=True, seed=args.seed)
+            return loader, loader
+        return ShardLoader(os.path.join(args.dataset_dir, 'val'), args.batch_size, 1, 0, shuffle=False,
+                           drop_last=False, seed=args.seed)
     import torchvision.datasets as datasets
     import torchvision.transforms as transforms
     norm = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
@@ -316,6 +329,18 @@ def make_dataloader(args, train=True):
         transforms.ToTensor(), norm]))
     return torch.utils.data.DataLoader(ds, batch_size=args.batch_size, shuffle=False,
                                        num_workers=args.num_dataloader_workers, pin_memory=True)
+
+
+def device_batch(args, batch, train=True):
+    """uint8 shard batches (``--data_format shards``): copy the bytes to the device and run the
+    crop / flip / normalisation there (``data.GpuAugment``); anything else passes through."""
+    if batch.dtype != torch.uint8:
+        return batch
+    aug = getattr(args, '_gpu_augment', None)
+    if aug is None:
+        from ..data import GpuAugment
+        aug = args._gpu_augment = GpuAugment(out_size=args.image_size, seed=args.seed * 7919 + args.rank)
+    return aug(batch.to(args.device, non_blocking=True), train=train)
 
 
 # --------------------------------------------------------------------------- #

@@ -227,6 +227,7 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
             if traced > args.trace_iters:       # bounded trace: dump once, then stop recording
                 log.info('trace written to %s' % tracing.disable().dump())
         target = target.to(dev, non_blocking=True)
+        batch = common.device_batch(args, batch, train=True)       # (uint8 shard batches only)
         if dev == 'cuda' and not batch.is_cuda and args.all_reduce:
             batch = batch.to(dev, non_blocking=True)
         t_data = time.time() - t_batch
@@ -299,7 +300,7 @@ def validate(args, val_loader, model, criterion, log):
     with torch.no_grad():
         for features, target in val_loader:
             target = target.to(dev, non_blocking=True)
-            features = features.to(dev, non_blocking=True)
+            features = common.device_batch(args, features, train=False).to(dev, non_blocking=True)
             if args.channels_last and dev == 'cuda':
                 features = features.contiguous(memory_format=torch.channels_last)
             with _autocast(args):

@@ -32,6 +32,7 @@ from .common import (CSVLog, Meter, accuracy, build_parser, finalize_args, fresh
                      init_model, learning_rate_at, make_dataloader, update_state)
 from ..experiment import ClusterManager, make_logger
 from ..utils import tracing
+from .common import device_batch
 
 
 def parse_args(argv=None):
@@ -163,6 +164,7 @@ def train(args, model, criterion, optimizer, batch_meter, data_meter, nn_meter, 
     i = 0
     for i, (batch, target) in enumerate(loader):
         target = target.to(dev, non_blocking=True)
+        batch = device_batch(args, batch, train=True)              # (uint8 shard batches only)
         t_data = time.time() - t_batch
         t_nn = time.time()
         if tracing.get_tracer().enabled and i >= args.trace_iters:
@@ -209,6 +211,7 @@ def validate(args, val_loader, model, criterion, log):
     with torch.no_grad():
         for features, target in val_loader:
             target = target.to(dev, non_blocking=True)
+            features = device_batch(args, features, train=False)
             with torch.autocast('cuda', dtype=torch.bfloat16,
                                 enabled=bool(args.amp and dev == 'cuda')):
                 output = model(features)

@@ -214,6 +214,13 @@ class GossipTrainer(object):
         self._ensure_static(batch_cpu, target_cpu)
         cs = self._copy_stream
         cs.wait_event(self._stage_free)
+        on_device = [t for t in (batch_cpu, target_cpu) if t.is_cuda]
+        if on_device:
+            # inputs produced on the GPU (e.g. data.GpuAugment output, a target moved by the caller):
+            # order the copy after the stream that produced them and keep their memory alive
+            cs.wait_stream(torch.cuda.current_stream(self.device))
+            for t in on_device:
+                t.record_stream(cs)
         with torch.cuda.stream(cs):
             self._stage.copy_(batch_cpu, non_blocking=True)
             self._stage_tgt.copy_(target_cpu, non_blocking=True)
