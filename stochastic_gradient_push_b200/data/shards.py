@@ -125,6 +125,8 @@ class ShardLoader(object):
         self.shuffle, self.drop_last, self.seed = shuffle, drop_last, int(seed)
         self.prefetch = max(1, int(prefetch))
         self.pin = torch.cuda.is_available() if pin is None else bool(pin)
+        self.use_native = True
+        self.gather_threads = int(os.environ.get('SGP_B200_LOADER_THREADS', 8))   # memcpy threads per batch
         self.sampler = self
         self._epoch = 0
         per_rank = self.total // self.world_size if drop_last else -(-self.total // self.world_size)
@@ -153,10 +155,30 @@ class ShardLoader(object):
                 perm = np.concatenate([perm, perm[:need]])
         return perm[self.rank::self.world_size]
 
+    def _native(self):
+        """the extension's multi-threaded row gather (``csrc/data_loader.cpp``), or None"""
+        if getattr(self, '_gather_fn', False) is False:
+            self._gather_fn = None
+            try:
+                from ..ops import native
+                if native.available():
+                    self._gather_fn = native.load().gather_rows_u8
+                    self._ptrs = [int(a.ctypes.data) for a in self.images]
+                    self._row_bytes = self.size * self.size * 3
+            except Exception:
+                self._gather_fn = None
+        return self._gather_fn
+
     def _gather(self, idx: np.ndarray, out: torch.Tensor):
-        """rows ``idx`` of the concatenated shards -> ``out`` (one fancy-index copy per shard)"""
-        dst = out.numpy()
+        """rows ``idx`` of the concatenated shards -> ``out``: a multi-threaded memcpy in the native
+        extension (GIL released), else one numpy fancy-index copy per shard"""
         shard = np.searchsorted(self.offsets, idx, side='right') - 1
+        fn = self._native() if self.use_native else None
+        if fn is not None:
+            fn(self._ptrs, self.counts, self._row_bytes, torch.from_numpy(shard.astype(np.int64)),
+               torch.from_numpy((idx - self.offsets[shard]).astype(np.int64)), out, self.gather_threads)
+            return
+        dst = out.numpy()
         for s in np.unique(shard):
             sel = np.nonzero(shard == s)[0]
             local = idx[sel] - self.offsets[s]

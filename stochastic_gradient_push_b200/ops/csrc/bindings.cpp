@@ -608,11 +608,13 @@ static void zero_(torch::Tensor x)
 
 void bind_bn(py::module& mod);   // bn_bindings.cpp
 void bind_vmm(py::module& mod);  // vmm_symm.cpp
+void bind_data(py::module& mod); // data_loader.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod)
 {
     bind_bn(mod);
     bind_vmm(mod);
+    bind_data(mod);
     mod.doc() = "sm_100a gossip kernels + symmetric-memory runtime";
     mod.def("symm_alloc", &symm_alloc, "allocate IPC-exportable device memory -> (uint8 tensor, handle)");
     mod.def("symm_open", &symm_open, "map a peer's allocation -> uint8 tensor");

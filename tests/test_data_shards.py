@@ -144,3 +144,24 @@ def test_cli_trains_from_shards_on_two_cpu_ranks(tmp_path, master_port):
         train_rows = [x.split(',') for x in rows if x.split(',')[1] != '-1']
         assert len(train_rows) >= 6 and all(float(x[12]) == float(x[12]) for x in train_rows)   # 6 iterations / epoch, finite loss
         assert any(x.split(',')[1] == '-1' for x in rows)                                        # validation ran
+
+
+def test_native_row_gather_matches_numpy(tmp_path):
+    try:
+        from stochastic_gradient_push_b200.ops import native
+        C = native.load()
+    except Exception as e:
+        pytest.skip('native extension unavailable: %s' % e)
+    imgs, _ = _fake_shards(tmp_path, n=300, size=24, shard_size=64)
+    a = ShardLoader(str(tmp_path), 32, 1, 0, seed=2, pin=False)
+    b = ShardLoader(str(tmp_path), 32, 1, 0, seed=2, pin=False)
+    b.use_native = False
+    assert a._native() is not None
+    for (xa, ya), (xb, yb) in zip(a, b):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    # bounds are checked before any byte is copied
+    out = torch.empty(2, 24 * 24 * 3, dtype=torch.uint8)
+    with pytest.raises(RuntimeError):
+        C.gather_rows_u8(a._ptrs, a.counts, a._row_bytes, torch.tensor([0, 99]), torch.tensor([0, 0]), out, 2)
+    with pytest.raises(RuntimeError):
+        C.gather_rows_u8(a._ptrs, a.counts, a._row_bytes, torch.tensor([0, 0]), torch.tensor([0, 64]), out, 2)
