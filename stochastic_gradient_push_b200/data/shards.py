@@ -262,7 +262,10 @@ class GpuAugment(object):
 
     def sample_boxes(self, n: int):
         """RandomResizedCrop parameters as fractions of the stored square image:
-        (cx, cy, w, h) in [0, 1], flip in {-1, +1} (host-side RNG: a few hundred bytes per batch)."""
+        (cx, cy, w, h) in [0, 1], flip in {-1, +1} (host-side RNG: a few hundred bytes per batch).
+        Area ~ U(scale), log-ratio ~ U(log ratio) as in torchvision; a box that does not fit is
+        clamped to the image instead of being re-drawn (torchvision retries 10 times, then falls back
+        to a centre crop), and the crops come from the stored centre square, not the full frame."""
         g = self._gen
         area = torch.empty(n).uniform_(self.scale[0], self.scale[1], generator=g)
         logr = torch.empty(n).uniform_(math.log(self.ratio[0]), math.log(self.ratio[1]), generator=g)
