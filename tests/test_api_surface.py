@@ -156,3 +156,16 @@ def test_cli_flags_and_registries(script):
         assert ("'%s'" % f) in src or ('"%s"' % f) in src, f
     for fn in ('main', 'train', 'validate', 'parse_args'):
         assert callable(getattr(mod, fn, None)), fn
+
+
+def test_reference_module_paths_import():
+    """`from gossip.graph_manager import ...`-style imports of reference users keep working"""
+    import importlib
+    for name in ('gossip.distributed', 'gossip.ad_psgd', 'gossip.gossiper', 'gossip.graph_manager',
+                 'gossip.mixing_manager', 'gossip.utils.helpers', 'gossip.utils.metering',
+                 'experiment_utils.cluster_manager', 'experiment_utils.helpers', 'experiment_utils.metering'):
+        importlib.import_module(name)
+    from gossip.graph_manager import Edge, GraphManager            # noqa: F401
+    from gossip.distributed import GossipDataParallel              # noqa: F401
+    from gossip.ad_psgd import BilatGossipDataParallel             # noqa: F401
+    from gossip.mixing_manager import MixingManager, UniformMixing  # noqa: F401
