@@ -402,17 +402,11 @@ public:
         fb_dev_ = reinterpret_cast<uint32_t*>(dp);
         for (int i = 0; i < 8; ++i) SGP_CUDA_CHECK(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
     }
-    ~BilatDaemon()
-    {
-        stop();
-        // the thread has drained the stream; release what the constructor created (errors are
-        // ignored: at interpreter exit the CUDA context may already be gone)
-        for (int i = 0; i < 8; ++i)
-            if (events_[i]) cudaEventDestroy(events_[i]);
-        if (stream_) cudaStreamDestroy(stream_);
-        if (fb_host_) cudaFreeHost(const_cast<uint32_t*>(fb_host_));
-        cudaGetLastError();
-    }
+    // (the stream, the 8 events and the 128-byte pinned feedback block are deliberately NOT released
+    // here: the destructor runs whenever Python's garbage collector gets to the object -- possibly
+    // while another stream of this thread is being captured into a CUDA graph, where cudaFreeHost
+    // (which synchronises the device) is illegal and would invalidate the capture)
+    ~BilatDaemon() { stop(); }
 
     void start()
     {
