@@ -193,9 +193,14 @@ class ShardLoader(object):
         q: 'queue.Queue' = queue.Queue(maxsize=self.prefetch)
         stop = threading.Event()
         pin = self.pin
+        # pinned allocations are made against the calling thread's current device; a new thread
+        # starts on device 0, which would create a stray context there from every rank
+        device = torch.cuda.current_device() if (pin and torch.cuda.is_available()) else None
 
         def work():
             try:
+                if device is not None:
+                    torch.cuda.set_device(device)
                 for b in range(nb):
                     if stop.is_set():
                         return
