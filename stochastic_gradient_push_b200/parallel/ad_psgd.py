@@ -421,6 +421,8 @@ class BilatGossipDataParallel(Module):
     # ------------------------------------------------------------------ #
     def _gossip_target(self):
         try:
+            if self.gossip_flat.is_cuda:         # a new thread starts on device 0
+                torch.cuda.set_device(self.gossip_flat.device)
             with torch.no_grad():
                 self._loop_c10d()
         except Exception as e:           # surfaced to the train thread
